@@ -1,0 +1,154 @@
+"""CPU tier: the real kernel sources (compiled for the host, one emulated thread per CTA) called
+through the C-ABI and the Python wrappers, checked against the numpy oracle and the
+reference-generated golden vectors.  The GPU tier (test_gpu_parity.py) repeats this on the B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle.slicq_oracle import SlicqOracle, snr_db
+
+
+@pytest.fixture(scope="module")
+def emu(request):
+    from tests.emu.emu_backend import EmuBackend
+    import xumx_slicq_b200.nsgt as nsgt_mod
+    old = nsgt_mod._BACKEND
+    nsgt_mod._BACKEND = EmuBackend()
+    yield nsgt_mod._BACKEND
+    nsgt_mod._BACKEND = old
+
+
+@pytest.fixture(scope="module")
+def base(emu):
+    from xumx_slicq_b200 import NSGTBase
+    return NSGTBase("bark", 262, 32.9, device="cpu")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return SlicqOracle(**common.BARK)
+
+
+def rel_err(c, r):
+    return float(np.abs(c - r).max() / np.abs(r).max())
+
+
+def test_forward_matches_reference_golden(base, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    buckets = [tuple(int(v) for v in b) for b in gold["buckets"]]
+    x = torch.from_numpy(common.small_input())
+    C = base.nsgt.forward((x,))                      # list of [S,N,F,M]
+    ref = common.unpack(gold["coefs"], buckets)
+    assert len(C) == 70
+    worst = 0.0
+    for c, r in zip(C, ref):
+        assert tuple(c.shape) == r.shape
+        worst = max(worst, rel_err(c.numpy(), r))
+    assert worst < 1e-5, worst                       # north-star tolerance: max relative coefficient error
+
+
+def test_inverse_matches_reference_golden(base, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    buckets = [tuple(int(v) for v in b) for b in gold["buckets"]]
+    ref = common.unpack(gold["coefs"], buckets)
+    T = common.SMALL_T
+    y = base.nsgt.backward([torch.from_numpy(np.ascontiguousarray(r)) for r in ref], T).numpy()
+    np.testing.assert_allclose(y, gold["y_roundtrip"], atol=5e-6)
+    P = common.perturb(ref)
+    yp = base.nsgt.backward([torch.from_numpy(p) for p in P], T).numpy()
+    np.testing.assert_allclose(yp, gold["y_perturbed"], atol=5e-6)
+    assert snr_db(gold["y_perturbed"], yp) > 120.0
+
+
+def test_roundtrip_snr_vs_reference(base, orc):
+    x = common.small_input()
+    xt = torch.from_numpy(x)
+    C = base.nsgt.forward((xt,))
+    y = base.nsgt.backward(C, x.shape[-1]).numpy()
+    ours = snr_db(x, y)
+    o32 = SlicqOracle(**common.BARK, dtype=np.float32)
+    theirs = snr_db(x, o32.backward(o32.forward(x), x.shape[-1]))
+    assert ours > theirs - 0.1, (ours, theirs)       # within 0.1 dB of an fp32 reference-style path
+    assert ours > 125.0
+
+
+def test_wrappers_layout_and_shapes(base, orc, golden_dir):
+    from xumx_slicq_b200 import make_filterbanks, ComplexNorm
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    nsgt, insgt = make_filterbanks(base)
+    x = torch.from_numpy(common.small_input()).view(1, 2, -1)
+    X = nsgt(x)
+    assert [list(t.shape) for t in X] == gold["wrapper_shapes"].tolist()
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in X)
+    W = orc.nsgt_sl(x.numpy().astype(np.float64))
+    for a, b in zip(X, W):
+        assert np.abs(a.numpy() - b).max() / np.abs(b).max() < 1e-5
+    mags = ComplexNorm()(X)
+    assert mags[1].shape == X[1].shape[:-1]
+    y = insgt(X, x.shape[-1])
+    assert y.shape == x.shape
+    assert snr_db(x.numpy(), y.numpy()) > 125.0
+    # 7-D input (targets, batch, channels, ...) as the separator passes it (separator.py:174)
+    Y4 = [torch.stack([t * s for s in (1.0, 0.5, 0.25, 0.125)]) for t in X]
+    y4 = insgt(Y4, x.shape[-1])
+    assert y4.shape == (4, 1, 2, x.shape[-1])
+    np.testing.assert_allclose(y4[2].numpy(), 0.25 * y.numpy(), atol=2e-6)
+    # inverse must not modify its input (the reference does)
+    before = [t.clone() for t in X]
+    insgt(X, x.shape[-1])
+    assert all(torch.equal(a, b) for a, b in zip(X, before))
+    # reference-style permuted (non-contiguous) inputs are accepted
+    Xp = [t.permute(0, 1, 3, 2, 4, 5).contiguous().permute(0, 1, 3, 2, 4, 5) for t in X]
+    assert not Xp[1].is_contiguous()
+    np.testing.assert_allclose(insgt(Xp, x.shape[-1]).numpy(), y.numpy(), atol=1e-7)
+
+
+def test_edge_lengths(base, golden_dir):
+    edge = np.load(os.path.join(golden_dir, "edge_lengths.npz"))
+    for T in (1, 4515, 9030, 9031, 18061):
+        xe = (np.random.RandomState(T).rand(1, T).astype(np.float32) * 2 - 1)
+        C = base.nsgt.forward((torch.from_numpy(xe),))
+        assert C[0].shape[0] == int(edge[f"S_{T}"])
+        E = np.asarray([float((c.abs() ** 2).sum()) for c in C])
+        np.testing.assert_allclose(E, edge[f"E_{T}"], rtol=1e-4, atol=1e-9)
+        y = base.nsgt.backward(C, T).numpy()
+        np.testing.assert_allclose(y, edge[f"y_{T}"], atol=5e-6)
+
+
+def test_slice_range_sharding_is_bitwise(base):
+    """slices [k0,k1) computed from the local sample range, one half-slice halo per
+    boundary; every output sample is a two-term sum, so the result equals the unsharded one bit for bit."""
+    nsg = base.nsgt
+    hop = nsg.sl_len // 2
+    T = 5 * hop + 1234
+    x = torch.from_numpy((np.random.RandomState(7).rand(2, T).astype(np.float32) * 2 - 1))
+    S = nsg.n_slices(T)
+    full = nsg.forward_rows(x)
+    y_full = nsg.backward_rows(full, T)
+    cuts = [0, 2, 5, S]
+    ys, halos = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lo, hi = max(0, (a - 1) * hop), min(T, b * hop)
+        part = nsg.forward_rows(x[:, lo:hi].contiguous(), k0=a, n_slices=b - a, t0=lo)
+        for pc, fc in zip(part, full):
+            assert torch.equal(pc, fc[:, :, a:b])
+        halo = torch.zeros(2, hop)
+        n_out = min(T, b * hop) - a * hop
+        ys.append(nsg.backward_rows(part, n_out, k0=a, t0=a * hop, halo_out=halo))
+        halos.append(halo)
+    for i in range(len(ys) - 1):          # the ONE message per boundary: right shard -> left shard
+        ys[i][:, -hop:] += halos[i + 1]
+    y = torch.cat(ys, dim=1)
+    assert y.shape == y_full.shape
+    assert torch.equal(y, y_full)
+
+
+def test_errors(base, emu):
+    from xumx_slicq_b200 import make_filterbanks
+    with pytest.raises(ValueError):
+        make_filterbanks(base, sample_rate=48000.0)
+    with pytest.raises(ValueError):
+        base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64)], 100)

@@ -1,0 +1,376 @@
+// C-ABI of libslicq (include/slicq.h): plan construction and the chunked launch sequences.
+//
+// forward  : per chunk of (row,slice) units   slice_fft_fwd_kernel -> bins_fwd_kernel
+// inverse  : per chunk                         bins_inv_kernel -> slice_fft_inv_kernel -> overlap_add_kernel
+// A chunk's intermediate spectra live in the caller-provided scratch buffer, sized so that it
+// stays resident in the 126 MB L2 (the spectra never make a round trip to HBM).
+#include "slicq_common.cuh"
+#include "../../include/slicq.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#ifdef SLICQ_EMU
+dim3 threadIdx, blockIdx, blockDim, gridDim;
+static unsigned char slicq_emu_smem_buf[256 * 1024] __attribute__((aligned(16)));
+unsigned char* slicq_emu_smem = slicq_emu_smem_buf;
+#endif
+
+extern "C" int slicq_launch_bins(const SlicqBinsParams* p, int n_tiles, int smem_bytes, int synth, cudaStream_t s);
+extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s);
+extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s);
+extern "C" int slicq_launch_ola(const SlicqOlaParams* p, cudaStream_t s);
+extern "C" int slicq_slice_smem_bytes(int L);
+
+namespace {
+
+thread_local std::string g_err;
+long long g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+struct FftPlan { int M, kind, A, B; };
+const FftPlan kFftPlans[] = {
+#define SLICQ_FFT_SIZE(M_, K_, A_, B_) {M_, K_, A_, B_},
+#include "fft_sizes.inc"
+#undef SLICQ_FFT_SIZE
+};
+
+const FftPlan* find_fft_plan(int M) {
+    for (size_t i = 0; i < sizeof(kFftPlans) / sizeof(kFftPlans[0]); ++i)
+        if (kFftPlans[i].M == M) return &kFftPlans[i];
+    return nullptr;
+}
+
+// shared-memory bytes one transform of this plan needs in a tile (max over analysis / synthesis)
+int fft_smem_per_transform(const FftPlan& f) {
+    if (f.kind == 1) return 0;
+    if (f.kind == 2) {
+        const int bp = (f.B % 2 == 0) ? f.B + 1 : f.B;
+        const int ap = (f.A % 2 == 0) ? f.A + 1 : f.A;
+        const int a = f.A * bp, b = f.B * ap;
+        return (a > b ? a : b) * 8;
+    }
+    return f.M * 8;  // kind 3: R * 2 * P floats
+}
+
+struct Bucket {
+    int M, first_bin, n_bins, G, tw_off, kind, A, B, smem_per_fft;
+};
+
+template <class T> int upload(const std::vector<T>& h, const T** d, std::vector<void*>& owned) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, h.size() * sizeof(T)) != cudaSuccess) return -1;
+    if (cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    owned.push_back(p);
+    *d = reinterpret_cast<const T*>(p);
+    return 0;
+}
+
+}  // namespace
+
+struct slicq_plan {
+    int L, N2, hop, J, sum_M;
+    std::vector<int> bin_M, bin_pos, bin_coff;
+    std::vector<Bucket> buckets;
+    SlicqDeviceTables dev;
+    std::vector<void*> owned;
+    int bins_smem;        // dynamic shared memory of the bins kernels
+    long long spec_stride_fwd;
+    long long chunk_bytes;
+};
+
+extern "C" int slicq_abi_version(void) { return SLICQ_ABI_VERSION; }
+extern "C" const char* slicq_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t slicq_launch_count(void) { return g_launches; }
+
+extern "C" void slicq_plan_destroy(slicq_plan* p) {
+    if (!p) return;
+    for (void* q : p->owned) cudaFree(q);
+    delete p;
+}
+
+extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
+    if (!t || !out) return fail(SLICQ_E_INVALID, "null argument");
+    *out = nullptr;
+    const int L = t->sl_len, J = t->n_bins;
+    if (L <= 0 || L % 4 != 0) return fail(SLICQ_E_INVALID, "sl_len must be a positive multiple of 4");
+    if (J < 2 || !t->bin_M || !t->bin_pos || !t->win_fwd || !t->win_inv || !t->tukey)
+        return fail(SLICQ_E_INVALID, "missing tables");
+    if (slicq_slice_smem_bytes(L) < 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "no slice-FFT kernel compiled for sl_len=%d (supported: 18060)", L);
+        return fail(SLICQ_E_UNSUPPORTED, buf);
+    }
+    slicq_plan* p = new slicq_plan();
+    p->L = L; p->N2 = L / 2; p->hop = L / 2; p->J = J;
+    p->bin_M.assign(t->bin_M, t->bin_M + J);
+    p->bin_pos.assign(t->bin_pos, t->bin_pos + J);
+    p->bin_coff.resize(J);
+    int off = 0;
+    for (int j = 0; j < J; ++j) {
+        const int M = p->bin_M[j], pos = p->bin_pos[j];
+        if (M < 4 || M % 4 != 0 || M > SLICQ_MAX_M || !find_fft_plan(M)) {
+            delete p;
+            return fail(SLICQ_E_UNSUPPORTED, "bin length M must be a multiple of 4 in [16, 292]");
+        }
+        if (pos % 2 != 0 || pos < 0 || pos > p->N2 || (j > 0 && pos <= p->bin_pos[j - 1])) {
+            delete p;
+            return fail(SLICQ_E_UNSUPPORTED, "bin positions must be even, increasing and within [0, L/2]");
+        }
+        p->bin_coff[j] = off;
+        off += M;
+    }
+    p->sum_M = off;
+    // The reference also accumulates the conjugate mirror of bins 1..J-2 at L - pos_j
+    // (nsigtf.py:63-80).  The kernels drop that pass, valid only if it never reaches [0, L/2].
+    for (int j = 1; j < J - 1; ++j) {
+        if (L - p->bin_pos[j] - p->bin_M[j] / 2 <= p->N2) {
+            delete p;
+            return fail(SLICQ_E_UNSUPPORTED, "a mirrored bin overlaps the kept half spectrum (unsupported scale)");
+        }
+    }
+    // buckets = maximal runs of equal M (nsgtf.py:66-78)
+    int tw_off = 0;
+    for (int j = 0; j < J; ++j) {
+        if (!p->buckets.empty() && p->buckets.back().M == p->bin_M[j]) {
+            p->buckets.back().n_bins++;
+            continue;
+        }
+        const FftPlan* f = find_fft_plan(p->bin_M[j]);
+        Bucket b;
+        b.M = p->bin_M[j]; b.first_bin = j; b.n_bins = 1; b.tw_off = tw_off;
+        b.kind = f->kind; b.A = f->A; b.B = f->B; b.smem_per_fft = fft_smem_per_transform(*f);
+        b.G = 1;
+        tw_off += b.M;
+        p->buckets.push_back(b);
+    }
+    if ((int)p->buckets.size() > SLICQ_MAX_BUCKETS) {
+        delete p;
+        return fail(SLICQ_E_UNSUPPORTED, "too many buckets");
+    }
+    // tile sizes: ~4096 coefficients per CTA, shared memory <= 64 KB
+    p->bins_smem = 0;
+    for (Bucket& b : p->buckets) {
+        int G = 4096 / (b.n_bins * b.M);
+        if (G < 1) G = 1;
+        if (G > 16) G = 16;
+        while (G > 1 && b.n_bins * G * b.smem_per_fft > 64 * 1024) --G;
+        b.G = G;
+        const int sm = b.n_bins * G * b.smem_per_fft;
+        if (sm > p->bins_smem) p->bins_smem = sm;
+    }
+
+    // ---- derived tables
+    std::vector<float> wf(p->sum_M), wi(p->sum_M), tuk(t->tukey, t->tukey + L);
+    for (int j = 0; j < J; ++j) {
+        const int M = p->bin_M[j], o = p->bin_coff[j];
+        const double sgn = ((p->bin_pos[j] / 2) % 2) ? -1.0 : 1.0;
+        for (int m = 0; m < M; ++m) {
+            wf[o + m] = (float)((double)t->win_fwd[o + m] * sgn / (double)M);
+            wi[o + m] = (float)((double)t->win_inv[o + m] * sgn * (double)M);
+        }
+    }
+    std::vector<float2> post(p->N2 / 2 + 1), tw(tw_off);
+    for (int k = 0; k <= p->N2 / 2; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)L;
+        post[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (const Bucket& b : p->buckets)
+        for (int j = 0; j < b.M; ++j) {
+            const double a = -2.0 * M_PI * (double)j / (double)b.M;
+            tw[b.tw_off + j] = make_float2((float)cos(a), (float)sin(a));
+        }
+    std::vector<unsigned short> jlo(p->N2 + 1);
+    std::vector<unsigned char> jcnt(p->N2 + 1);
+    for (int f = 0; f <= p->N2; ++f) {
+        int first = -1, last = -1, n = 0;
+        for (int j = 0; j < J; ++j) {
+            const int d = f - p->bin_pos[j], h = p->bin_M[j] / 2;
+            if (d >= -h && d < h) { if (first < 0) first = j; last = j; ++n; }
+        }
+        if (n == 0 || last - first + 1 != n || n > 255) {
+            delete p;
+            return fail(SLICQ_E_UNSUPPORTED, "spectrum position not covered by a consecutive run of bins");
+        }
+        jlo[f] = (unsigned short)first;
+        jcnt[f] = (unsigned char)n;
+    }
+
+    SlicqDeviceTables& d = p->dev;
+    memset(&d, 0, sizeof d);
+    d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
+    int rc = 0;
+    rc |= upload(tuk, &d.tukey, p->owned);
+    rc |= upload(wf, &d.wf, p->owned);
+    rc |= upload(wi, &d.wi, p->owned);
+    rc |= upload(p->bin_pos, &d.bin_pos, p->owned);
+    rc |= upload(p->bin_M, &d.bin_M, p->owned);
+    rc |= upload(p->bin_coff, &d.bin_coff, p->owned);
+    rc |= upload(post, &d.post_tw, p->owned);
+    rc |= upload(tw, &d.tw, p->owned);
+    rc |= upload(jlo, &d.jlo, p->owned);
+    rc |= upload(jcnt, &d.jcnt, p->owned);
+    if (rc) {
+        slicq_plan_destroy(p);
+        return fail(SLICQ_E_CUDA, "device table upload failed");
+    }
+    p->spec_stride_fwd = p->N2 + 2;  // N2+1 bins, padded to an even count (16-byte rows)
+    const char* env = getenv("SLICQ_CHUNK_MB");
+    long long mb = env ? atoll(env) : 40;
+    if (mb < 1) mb = 1;
+    p->chunk_bytes = mb << 20;
+    *out = p;
+    return SLICQ_OK;
+}
+
+extern "C" int slicq_plan_n_buckets(const slicq_plan* p) { return p ? (int)p->buckets.size() : SLICQ_E_INVALID; }
+
+extern "C" int slicq_plan_bucket_info(const slicq_plan* p, int b, int32_t* first_bin, int32_t* n_bins, int32_t* M) {
+    if (!p || b < 0 || b >= (int)p->buckets.size()) return fail(SLICQ_E_INVALID, "bad bucket index");
+    if (first_bin) *first_bin = p->buckets[b].first_bin;
+    if (n_bins) *n_bins = p->buckets[b].n_bins;
+    if (M) *M = p->buckets[b].M;
+    return SLICQ_OK;
+}
+
+extern "C" int64_t slicq_plan_num_slices(const slicq_plan* p, int64_t T) {
+    if (!p || T < 0) return SLICQ_E_INVALID;
+    const int64_t hh = p->L / 4;
+    const int64_t nblk = (T + hh - 1) / hh;  // quarter-hop blocks (slicing.py:34-42)
+    return (nblk + 1) / 2 + 1;               // slicing.py:49,61-72
+}
+
+namespace {
+long long bytes_per_unit(const slicq_plan* p, int inverse) {
+    if (!inverse) return p->spec_stride_fwd * 8;
+    return (long long)p->sum_M * 8 + (long long)p->L * 4;
+}
+long long chunk_units(const slicq_plan* p, int inverse) {
+    long long c = p->chunk_bytes / bytes_per_unit(p, inverse);
+    return c < 1 ? 1 : c;
+}
+}  // namespace
+
+extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse) {
+    if (!p || n_rows <= 0 || n_slices <= 0) return 0;
+    long long units = n_rows * n_slices;
+    const long long c = chunk_units(p, inverse);
+    if (units > c) units = c;
+    return (size_t)(units * bytes_per_unit(p, inverse) + 256);
+}
+
+namespace {
+int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqBinsParams& bp, int n_rs) {
+    int tiles = 0;
+    bp.n_buckets = (int)p->buckets.size();
+    for (size_t i = 0; i < p->buckets.size(); ++i) {
+        const Bucket& b = p->buckets[i];
+        SlicqBucketArg& a = bp.b[i];
+        a.ptr = reinterpret_cast<float2*>(views[i].ptr);
+        a.s_row = views[i].s_row; a.s_bin = views[i].s_bin; a.s_slice = views[i].s_slice;
+        a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.G = b.G; a.tw_off = b.tw_off;
+        a.kind = b.kind; a.A = b.A; a.B = b.B; a.pad_ = 0;
+        a.tile_start = tiles;
+        tiles += (n_rs + b.G - 1) / b.G;
+    }
+    return tiles;
+}
+}  // namespace
+
+extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                             int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                             const slicq_bucket_view* buckets, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!p || !x || !buckets) return fail(SLICQ_E_INVALID, "null argument");
+    if (n_rows <= 0 || n_slices <= 0 || n_samples < 0) return fail(SLICQ_E_INVALID, "bad shape");
+    if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
+    if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 0) || !scratch)
+        return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
+    for (size_t i = 0; i < p->buckets.size(); ++i)
+        if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long units = n_rows * n_slices, cu = chunk_units(p, 0);
+    float2* H = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
+    SlicqSliceParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.t = p->dev; sp.x = x; sp.x_row_stride = x_row_stride; sp.T = n_samples; sp.t0 = t0; sp.k0 = k0;
+    sp.spec = H; sp.spec_stride = p->spec_stride_fwd; sp.S = (int)n_slices;
+    SlicqBinsParams* bp = new SlicqBinsParams();
+    bp->t = p->dev; bp->spec = H; bp->spec_stride = p->spec_stride_fwd; bp->S = (int)n_slices;
+    int rc = 0;
+    for (long long u0 = 0; u0 < units && rc == 0; u0 += cu) {
+        const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
+        sp.n_rs = n; sp.rs0 = (int)u0;
+        rc = slicq_launch_slice_fwd(&sp, s);
+        ++g_launches;
+        if (rc) break;
+        bp->n_rs = n; bp->rs0 = (int)u0;
+        const int tiles = fill_bins_params(p, buckets, *bp, n);
+        rc = slicq_launch_bins(bp, tiles, p->bins_smem, 0, s);
+        ++g_launches;
+    }
+    delete bp;
+    if (rc) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "kernel launch failed: %s", rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "unsupported");
+        return fail(SLICQ_E_CUDA, buf);
+    }
+    return SLICQ_OK;
+}
+
+extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* buckets, int64_t n_rows,
+                             int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
+                             int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!p || !y || !buckets) return fail(SLICQ_E_INVALID, "null argument");
+    if (n_rows <= 0 || n_slices <= 0 || length < 0) return fail(SLICQ_E_INVALID, "bad shape");
+    if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
+    if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 1) || !scratch)
+        return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
+    for (size_t i = 0; i < p->buckets.size(); ++i)
+        if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long units = n_rows * n_slices, cu = chunk_units(p, 1);
+    const long long nu = units < cu ? units : cu;
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
+    float2* T = reinterpret_cast<float2*>(base);
+    float* U = reinterpret_cast<float*>(base + nu * (long long)p->sum_M * 8);
+    SlicqBinsParams* bp = new SlicqBinsParams();
+    bp->t = p->dev; bp->spec = T; bp->spec_stride = p->sum_M; bp->S = (int)n_slices;
+    SlicqSliceParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->sum_M; sp.u = U; sp.S = (int)n_slices;
+    SlicqOlaParams op;
+    memset(&op, 0, sizeof op);
+    op.u = U; op.L = p->L; op.hop = p->hop; op.S = (int)n_slices; op.y = y; op.y_row_stride = y_row_stride;
+    op.length = length; op.k0 = k0; op.t0 = t0; op.halo_out = halo_out; op.scale = 1.f;
+    int rc = 0;
+    for (long long u0 = 0; u0 < units && rc == 0; u0 += cu) {
+        const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
+        bp->n_rs = n; bp->rs0 = (int)u0;
+        const int tiles = fill_bins_params(p, buckets, *bp, n);
+        rc = slicq_launch_bins(bp, tiles, p->bins_smem, 1, s);
+        ++g_launches;
+        if (rc) break;
+        sp.n_rs = n; sp.rs0 = (int)u0;
+        rc = slicq_launch_slice_inv(&sp, s);
+        ++g_launches;
+        if (rc) break;
+        op.n_rs = n; op.rs0 = (int)u0;
+        rc = slicq_launch_ola(&op, s);
+        ++g_launches;
+    }
+    delete bp;
+    if (rc) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "kernel launch failed: %s", rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "unsupported");
+        return fail(SLICQ_E_CUDA, buf);
+    }
+    return SLICQ_OK;
+}

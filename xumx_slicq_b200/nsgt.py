@@ -1,0 +1,234 @@
+"""`NSGT_sliced` -- host-side mirror of the reference's sliced transform driver
+(xumx_slicq_v2/nsgt/slicq.py:70-243) on top of the sm_100a kernels in libslicq.so.
+
+Same constructor arguments, attributes (``sl_len, tr_area, fs, frqs, q, g, gd, M, rfbas, wins,
+nn, sl, fbins_actual, ncoefs``) and methods (``forward((sig,))``, ``backward(cseq, length)``,
+``coef_factor``, ``coef_factors()``) as the reference for the configuration its wrappers use
+(``real=True, multichannel=True, reducedform=0, recwnd=False``; transforms.py:60-68).  The
+computation itself is one call into the C-ABI (include/slicq.h); there is no torch.fft, no CPU
+path and no fallback -- tensors must live on a CUDA device.
+
+Coefficient layout: all buckets of one call share ONE allocation; bucket b is the contiguous
+block ``[N, F_b, S, M_b]`` complex64 (the layout the CDAE model consumes).  ``forward`` returns
+the reference's ``[S, N, F_b, M_b]`` axis order as permuted views of that block.
+"""
+from __future__ import annotations
+
+import copy
+from math import ceil
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import plan as _plan
+
+
+class _CudaBackend:
+    """The only backend of the product: libslicq.so on a CUDA device."""
+
+    name = "cuda"
+
+    def lib(self):
+        return _cabi.load()
+
+    def check(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError(
+                "xumx_slicq_b200 runs on CUDA devices only (hand-written sm_100a kernels, no CPU fallback); "
+                f"got a tensor on '{t.device}'")
+
+    def stream(self, device: torch.device) -> int:
+        return torch.cuda.current_stream(device).cuda_stream
+
+    def device_guard(self, device: torch.device):
+        return torch.cuda.device(device)
+
+
+_BACKEND = _CudaBackend()
+
+
+class _PlanCache:
+    """Per-device `slicq_plan` handles, created lazily; never copied (ctypes handles)."""
+
+    def __init__(self):
+        self.plans = {}
+
+    def __deepcopy__(self, memo):
+        return _PlanCache()
+
+    def get(self, tables, device: torch.device) -> _cabi.Plan:
+        key = (device.type, device.index)
+        p = self.plans.get(key)
+        if p is None:
+            with _BACKEND.device_guard(device):
+                p = _cabi.Plan(tables, _BACKEND.lib())
+            self.plans[key] = p
+        return p
+
+
+class NSGT_sliced(torch.nn.Module):
+    def __init__(self, scale, sl_len, tr_area, fs, min_win=16, Qvar=1, real=False, recwnd=False,
+                 reducedform=0, multichannel=False, dtype=torch.float32, device="cpu"):
+        # argument checks of slicq.py:86-94
+        assert fs > 0
+        assert sl_len > 0
+        assert tr_area >= 0
+        assert sl_len > tr_area * 2
+        assert min_win > 0
+        assert 0 <= reducedform <= 2
+        assert sl_len % 4 == 0
+        assert tr_area % 2 == 0
+        super().__init__()
+        if not real or not multichannel or reducedform != 0 or recwnd or dtype != torch.float32:
+            raise NotImplementedError(
+                "the B200 path implements the configuration the xumx-sliCQ wrappers use: "
+                "real=True, multichannel=True, reducedform=0, recwnd=False, float32")
+        self.device = torch.device(device)
+        self.sl_len, self.tr_area, self.fs = int(sl_len), int(tr_area), fs
+        self.real, self.userecwnd, self.reducedform, self.multichannel = real, recwnd, reducedform, multichannel
+        self.scale = scale
+        self.tables = _plan.design(scale, fs, self.sl_len, self.tr_area, min_win=min_win, qvar=Qvar)
+        t = self.tables
+        self.frqs, self.q = torch.from_numpy(t.frqs), torch.from_numpy(t.q)
+        self.M = torch.from_numpy(t.M_all.copy())
+        self.rfbas = torch.from_numpy(t.rfbas_all.copy())
+        self.sl = slice(0, t.n_bins)
+        self.fbins_actual = t.n_bins
+        self.ncoefs = t.ncoefs
+        self.nn = self.sl_len
+        self._cache = _PlanCache()
+        self._anchor = torch.zeros(1, device=self.device) if self.device.type == "cpu" else None
+        if self.device.type != "cpu":
+            self._anchor = torch.zeros(1, device=self.device)
+
+    # -- reference-visible window tables (host copies, for inspection / visualisation) -----
+    def _split(self, flat: np.ndarray) -> List[torch.Tensor]:
+        out, o = [], 0
+        for m in self.tables.bin_M:
+            out.append(torch.from_numpy(flat[o:o + int(m)].copy()))
+            o += int(m)
+        return out
+
+    @property
+    def g(self) -> List[torch.Tensor]:
+        return self._split(self.tables.win_fwd)
+
+    @property
+    def gd(self) -> List[torch.Tensor]:
+        return self._split(self.tables.win_inv)
+
+    @property
+    def wins(self) -> List[torch.Tensor]:
+        out = []
+        for m, c in zip(self.tables.bin_M, self.tables.bin_pos):
+            out.append(torch.from_numpy((np.arange(-(int(m) // 2), int(m) - int(m) // 2) + int(c)) % self.nn))
+        return out
+
+    # -- device plumbing (nn.Module.to / .cuda / .cpu), slicq.py:175-180 -------------------
+    def _apply(self, fn, *a, **k):
+        self._anchor = fn(self._anchor)
+        self.device = self._anchor.device
+        return self
+
+    def plan(self, device: torch.device | None = None) -> _cabi.Plan:
+        return self._cache.get(self.tables, device or self.device)
+
+    # -- layout helpers ---------------------------------------------------------------------
+    def n_slices(self, n_samples: int) -> int:
+        return self.tables.num_slices(int(n_samples))
+
+    def alloc_coefficients(self, n_rows: int, n_slices: int, device) -> tuple:
+        """One slab for all buckets; returns (slab, [bucket tensors [N,F,S,M] complex64])."""
+        t = self.tables
+        slab = torch.empty(n_rows * n_slices * t.sum_M, dtype=torch.complex64, device=device)
+        out, o = [], 0
+        for (_, nb, M) in t.buckets:
+            n = n_rows * nb * n_slices * M
+            out.append(slab[o:o + n].view(n_rows, nb, n_slices, M))
+            o += n
+        return slab, out
+
+    @staticmethod
+    def _view_of(c: torch.Tensor) -> tuple:
+        """(ptr, s_row, s_bin, s_slice) of a complex [N,F,S,M] tensor with contiguous M."""
+        return (c.data_ptr(), c.stride(0), c.stride(1), c.stride(2))
+
+    # -- analysis ---------------------------------------------------------------------------
+    def forward_rows(self, x: torch.Tensor, k0: int = 0, n_slices: int | None = None, t0: int = 0) -> List[torch.Tensor]:
+        """x [N, T] float32 -> list of contiguous [N, F_b, S, M_b] complex64 (canonical layout).
+
+        ``k0 / n_slices / t0`` select a slice range of a longer signal (shard of a long track):
+        local slice i is global slice k0+i and x[:, 0] is global sample t0."""
+        _BACKEND.check(x)
+        if x.dim() != 2:
+            raise ValueError("expected [rows, samples]")
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)  # the reference computes in float32 regardless of input dtype
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        N, T = x.shape
+        S = self.n_slices(T) if n_slices is None else int(n_slices)
+        plan = self.plan(x.device)
+        with _BACKEND.device_guard(x.device):
+            slab, out = self.alloc_coefficients(N, S, x.device)
+            nbytes = plan.scratch_bytes(N, S, False)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            plan.forward(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S,
+                         [self._view_of(c) for c in out], scratch.data_ptr(), nbytes,
+                         _BACKEND.stream(x.device))
+        return out
+
+    def forward(self, sig: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """slicq.py:182-196: ``sig`` is a 1-tuple holding [N, T]; returns list of [S, N, F_b, M_b]."""
+        (x,) = sig
+        return [c.permute(2, 0, 1, 3) for c in self.forward_rows(x)]
+
+    # -- synthesis --------------------------------------------------------------------------
+    def backward_rows(self, coefs: Sequence[torch.Tensor], length: int, k0: int = 0, t0: int = 0,
+                      halo_out: torch.Tensor | None = None) -> torch.Tensor:
+        """list of complex [N, F_b, S, M_b] (any strides, M contiguous) -> [N, length] float32."""
+        t = self.tables
+        if len(coefs) != len(t.buckets):
+            raise ValueError(f"expected {len(t.buckets)} coefficient buckets, got {len(coefs)}")
+        c0 = coefs[0]
+        _BACKEND.check(c0)
+        N, S = c0.shape[0], c0.shape[2]
+        views = []
+        keep = []
+        for c, (_, nb, M) in zip(coefs, t.buckets):
+            if c.dtype != torch.complex64:
+                c = c.to(torch.complex64)
+            if tuple(c.shape) != (N, nb, S, M):
+                raise ValueError(f"bucket shape {tuple(c.shape)} != {(N, nb, S, M)}")
+            if c.stride(3) != 1 and M > 1:
+                c = c.contiguous()
+            keep.append(c)
+            views.append(self._view_of(c))
+        length = int(length)
+        avail = (int(k0) + S) * t.hop - int(t0)
+        out_len = max(0, min(length, avail))  # reblock(fulllast=False): at most the samples that exist
+        plan = self.plan(c0.device)
+        with _BACKEND.device_guard(c0.device):
+            y = torch.empty((N, out_len), dtype=torch.float32, device=c0.device)
+            nbytes = plan.scratch_bytes(N, S, True)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=c0.device)
+            plan.inverse(views, N, S, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len, int(t0),
+                         halo_out.data_ptr() if halo_out is not None else 0,
+                         scratch.data_ptr(), nbytes, _BACKEND.stream(c0.device))
+        del keep
+        return y
+
+    def backward(self, cseq: Sequence[torch.Tensor], length: int) -> torch.Tensor:
+        """slicq.py:198-230: list of [S, N, F_b, M_b] complex -> [N, length].
+        Unlike the reference this does not modify ``cseq`` in place."""
+        return self.backward_rows([c.permute(1, 2, 0, 3) for c in cseq], length)
+
+    # -- bookkeeping ------------------------------------------------------------------------
+    @property
+    def coef_factor(self) -> float:  # slicq.py:232-234
+        return float(self.ncoefs) / self.sl_len
+
+    def coef_factors(self) -> List[float]:  # slicq.py:236-243
+        return [float(int(ceil(float(m) / m)) * m) / self.sl_len for m in map(int, self.tables.bin_M)]

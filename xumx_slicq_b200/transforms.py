@@ -1,0 +1,136 @@
+"""Drop-in replacements for the reference's transform wrappers (xumx_slicq_v2/transforms.py).
+
+Same names, call signatures, attributes and ragged per-bucket output layout, so the CDAE model,
+separator, inference and export code of xumx-sliCQ-V2 run on the B200 kernels unchanged:
+
+    make_filterbanks(nsgt_base, sample_rate=44100.0) -> (NSGT_SL, INSGT_SL)      transforms.py:11-18
+    NSGTBase(scale, fbins, fmin, fmax=22050.0, fgamma=15.0, fs=44100.0, device)   transforms.py:21-94
+    NSGT_SL(nsgt).forward(x[..., T])  -> list of [..., F_b, S, M_b, 2] float32    transforms.py:97-131
+    INSGT_SL(nsgt).forward(X_list, length) -> [..., length] float32               transforms.py:134-178
+    ComplexNorm().forward(list | Tensor)                                          transforms.py:181-208
+
+Differences that are deliberate: outputs are contiguous per bucket (the reference
+returns permuted views of [S,N,F,M] storage), INSGT_SL does not modify its input in place, and
+there is no CPU execution path -- CPU inputs handed to a CUDA-resident module (the reference's
+`predict_input_size` does that, transforms.py:83-89) are moved to the module's device.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .nsgt import NSGT_sliced
+from .plan import make_scale
+
+
+def make_filterbanks(nsgt_base, sample_rate=44100.0):
+    if sample_rate != 44100.0:
+        raise ValueError("i was lazy and harcoded a lot of 44100.0, forgive me")  # transforms.py:12-13
+    return NSGT_SL(nsgt_base), INSGT_SL(nsgt_base)
+
+
+class NSGTBase(nn.Module):
+    def __init__(self, scale, fbins, fmin, fmax=22050.0, fgamma=15.0, fs=44100.0, device="cuda"):
+        super().__init__()
+        self.fbins = fbins
+        self.fmin = fmin
+        self.fmax = fmax
+        self.scl = make_scale(scale, self.fmin, self.fmax, self.fbins, fgamma)
+        self.sllen, self.trlen = self.scl.suggested_sllen_trlen(fs)
+        scale_to_print = scale if scale != "vqlog" else f"vqlog (gamma={fgamma})"
+        print(f"scale={scale_to_print}, fbins={fbins}, fmin={fmin:.2f}, fmax={fmax:.2f}, "
+              f"sllen={self.sllen}, trlen={self.trlen}")
+        self.nsgt = NSGT_sliced(self.scl, self.sllen, self.trlen, fs, real=True, multichannel=True, device=device)
+        self.M = self.nsgt.ncoefs
+        self.fs = fs
+        self.fbins_actual = self.nsgt.fbins_actual
+
+    def max_bins(self, bandwidth):  # convert hz bandwidth into bins (transforms.py:73-78)
+        if bandwidth is None or bandwidth < 0:
+            return None
+        freqs, _ = self.scl()
+        freqs = torch.from_numpy(freqs)
+        max_bin = min(torch.argwhere(freqs > bandwidth))[0]
+        return max_bin + 1
+
+    def predict_input_size(self, batch_size, nb_channels, seq_dur_s):
+        fwd = NSGT_SL(self)
+        x = torch.rand((batch_size, nb_channels, int(seq_dur_s * self.fs)), dtype=torch.float32)
+        return fwd(x), x
+
+    def _apply(self, fn, *a, **k):
+        self.nsgt._apply(fn)
+        return self
+
+
+def _module_device(nsgt_base) -> torch.device:
+    return nsgt_base.nsgt.device
+
+
+class NSGT_SL(nn.Module):
+    def __init__(self, nsgt):
+        super().__init__()
+        self.nsgt = nsgt
+
+    def _apply(self, fn, *a, **k):
+        self.nsgt._apply(fn)
+        return self
+
+    def forward(self, x: Tensor) -> List[Tensor]:
+        """x [..., T] -> list over buckets of [..., F_b, S, M_b, 2] (last axis re, im)."""
+        shape = x.size()
+        dev = _module_device(self.nsgt)
+        if x.device != dev and x.device.type == "cpu":
+            x = x.to(dev)
+        x = x.contiguous().view(-1, shape[-1])
+        C = self.nsgt.nsgt.forward_rows(x)
+        lead = tuple(shape[:-1])
+        return [torch.view_as_real(c).view(lead + tuple(c.shape[1:]) + (2,)) for c in C]
+
+
+class INSGT_SL(nn.Module):
+    """Inverse wrapper.  X_list: per bucket [B, C, F_b, S, M_b, 2] or [T, B, C, F_b, S, M_b, 2]."""
+
+    def __init__(self, nsgt):
+        super().__init__()
+        self.nsgt = nsgt
+
+    def _apply(self, fn, *a, **k):
+        self.nsgt._apply(fn)
+        return self
+
+    def forward(self, X_list, length: int) -> Tensor:
+        dev = _module_device(self.nsgt)
+        cs = []
+        lead = None
+        for X in X_list:
+            if X.device != dev and X.device.type == "cpu":
+                X = X.to(dev)
+            if X.dtype != torch.float32:
+                X = X.to(torch.float32)
+            if X.stride(-1) != 1 or X.stride(-2) != 2:
+                X = X.contiguous()
+            Xc = torch.view_as_complex(X)            # [*lead, F, S, M]
+            lead = tuple(Xc.shape[:-3])
+            try:
+                Xc = Xc.view((-1,) + tuple(Xc.shape[-3:]))
+            except RuntimeError:                      # leading dims not collapsible: make it so
+                Xc = Xc.contiguous().view((-1,) + tuple(Xc.shape[-3:]))
+            cs.append(Xc)
+        y = self.nsgt.nsgt.backward_rows(cs, length)
+        return y.view(*lead, -1)
+
+
+class ComplexNorm(nn.Module):
+    """Magnitude of a ragged sliCQT list or a single tensor (transforms.py:181-208)."""
+
+    def forward(self, spec):
+        if isinstance(spec, list):
+            return [torch.abs(torch.view_as_complex(c)) for c in spec]
+        elif isinstance(spec, Tensor):
+            return self.forward([spec])[0]
+        else:
+            raise ValueError(f"unsupported type for 'spec': {type(spec)}")
