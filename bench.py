@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""Benchmark of the sliCQT hot path (BASELINE.json metric: fwd+inv audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: the sliCQT path of a realtime-model demix of one synthetic 30 s
+44.1 kHz stereo mixture -- ONE forward (2 rows x 148 slices) and ONE inverse of the 4 target
+estimates (8 rows x 148 slices).  The 4 target coefficient sets stand in for the model output
+(mixture coefficients times per-target gains, generated before the timed region; the CDAE model
+is out of scope).  One step = one such pass per GPU (weak scaling: every rank
+owns its own mixture, tracks are independent, no data-path collective).
+
+Printed JSON line (rank 0): see the keys documented in DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+FS = 44100
+SECONDS = 30.0
+T = int(SECONDS * FS)            # 1 323 000 samples
+N_TARGETS = 4
+GAINS = (0.9, 0.6, 0.4, 0.2)     # stand-in "soft masks" of the four targets
+SCALE = dict(scale="bark", fbins=262, fmin=32.9)
+# algorithmic HBM bytes: per (row, slice) and direction
+B_IN = 9030 * 4                  # new input / output samples of one hop
+B_COEF = 18640 * 8               # complex64 coefficients
+B_UNIT = B_IN + B_COEF           # 185 240
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (pynvml, nvidia-smi fallback)."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _reasons(self, mask: int):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        return {k for k, bit in names.items() if mask & bit}
+
+    def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reasons |= self._reasons(int(mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps: int, warmup: int, sample_seconds: float):
+    """The reference's algorithm on the host cores: the NumPy/pocketfft port in oracle/ (the
+    reference is pure Python/torch and cannot travel to the GPU box).  fp32 storage
+    like the reference, all host threads for the FFTs."""
+    from oracle.slicq_oracle import SlicqOracle
+    cores = os.cpu_count() or 1
+    orc = SlicqOracle(**SCALE, dtype=np.float32, workers=cores)
+    Ts = int(sample_seconds * FS)
+    rs = np.random.RandomState(0)
+    x = (rs.rand(2, Ts).astype(np.float32) * 2 - 1)
+
+    def step():
+        C = orc.forward(x)
+        Y = [np.concatenate([c * np.float32(g) for g in GAINS], axis=1) for c in C]   # [S, 4*2, F, M]
+        return orc.backward(Y, Ts)
+
+    for _ in range(max(1, warmup)):
+        step()
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+    dt = float(np.mean(times))
+    return sample_seconds / dt, dt, cores, f"{sample_seconds:g} s stereo mixture: 1 forward (2 rows) + inverse of 4 targets (8 rows)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="30 s mixtures per GPU per step")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    base_cfg = {"workload": "configs[1]: sliCQT path of a realtime demix of one synthetic 30 s 44.1 kHz stereo "
+                            "mixture (1 forward of 2 rows x 148 slices + inverse of 4 targets = 8 rows x 148 slices), "
+                            "Bark(262, 32.9 Hz), sllen 18060",
+                "mixtures_per_gpu_per_step": args.batch, "parallelism": f"tracks x{max(world, args.gpus)}",
+                "l2": "inputs+outputs of one step (>= 330 MB) exceed the 126 MB L2 and an extra 256 MB buffer is "
+                      "written between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        steps = max(1, min(args.steps, 5))
+        val, dt, cores, sample = cpu_reference_arm(steps, min(args.warmup, 1), args.cpu_sample_seconds)
+        print(json.dumps({
+            "impl": "reference", "metric": "sliCQT fwd+inv audio-sec/sec", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_cfg,
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from xumx_slicq_b200 import NSGTBase, make_filterbanks, _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        base = NSGTBase(SCALE["scale"], SCALE["fbins"], SCALE["fmin"], device=dev)
+    nsg = base.nsgt
+    nsgt, insgt = make_filterbanks(base)
+    B = args.batch
+    S = nsg.n_slices(T)
+    rows_f, rows_i = 2 * B, 2 * B * N_TARGETS
+
+    # ---- synthetic inputs, resident in HBM before the timed region
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x = torch.rand(rows_f, T, device=dev, generator=gen) * 2 - 1
+    Cmix = nsg.forward_rows(x)
+    # model-output stand-in: [targets*rows, F, S, M] per bucket (targets-major like separator.py:174)
+    Y = [torch.cat([c * g for g in GAINS], dim=0).contiguous() for c in Cmix]
+    del Cmix
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    plan = nsg.plan(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    # preallocated outputs + scratch so that the timed region is kernels only
+    slab, Cout = nsg.alloc_coefficients(rows_f, S, dev)
+    views_f = [nsg._view_of(c) for c in Cout]
+    views_i = [nsg._view_of(c) for c in Y]
+    sb_f, sb_i = plan.scratch_bytes(rows_f, S, False), plan.scratch_bytes(rows_i, S, True)
+    scratch = torch.empty(max(sb_f, sb_i), dtype=torch.uint8, device=dev)
+    yout = torch.empty(rows_i, T, device=dev)
+
+    def step_device():
+        plan.forward(x.data_ptr(), rows_f, x.stride(0), T, 0, 0, S, views_f, scratch.data_ptr(), sb_f,
+                     stream.cuda_stream)
+        plan.inverse(views_i, rows_i, S, 0, yout.data_ptr(), yout.stride(0), T, 0, 0, scratch.data_ptr(), sb_i,
+                     stream.cuda_stream)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = plan.launch_count()
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    barrier()
+    launches = plan.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = np.asarray([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
+    ms_per_step = float(step_ms.mean())
+    t = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item())
+    n_gpus = world
+    audio_s = SECONDS * B * n_gpus
+    value = audio_s / (ms_per_step * 1e-3)
+
+    # ---- per-kernel CUDA-event timing (separate pass; event records between kernels are not free)
+    _cabi.profile_enable(True)
+    nprof = 5
+    for _ in range(nprof):
+        flush.fill_(1)
+        step_device()
+    torch.cuda.synchronize(dev)
+    prof = _cabi.profile_read()
+    _cabi.profile_enable(False)
+    units_f, units_i = rows_f * S, rows_i * S
+    kern = {}
+    alg = {"slice_fft_fwd": B_IN * units_f, "bins_fwd": B_COEF * units_f, "bins_inv": B_COEF * units_i,
+           "slice_fft_inv": 0, "overlap_add": B_IN * units_i}
+    tot_ms = 0.0
+    for k, (ms, n) in prof.items():
+        per_step = ms / nprof
+        tot_ms += per_step
+        kern[k] = {"ms_per_step": round(per_step, 4), "launches_per_step": n // nprof,
+                   "hbm_bytes_per_step": alg[k]}
+    peak, peak_src = load_peaks()
+    alg_step = B_UNIT * (units_f + units_i)
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    achieved = alg_step / (ms_per_step * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": None,
+        "scope": "whole path: algorithmic bytes of one step (185 240 B per (row,slice) and direction) / "
+                 "CUDA-event time of the step (all five kernels)",
+        "peak_source": peak_src, "algorithmic_bytes_per_step": alg_step,
+        "dominant_kernel": dom, "kernel_share": {k: round(v["ms_per_step"] / max(tot_ms, 1e-9), 3) for k, v in kern.items()},
+        "kernels": kern,
+    }
+
+    # ---- end to end through the public wrappers with HOST buffers (pinned), every step:
+    #      H2D of the mixture, NSGT_SL, target stand-in, INSGT_SL, D2H of the 4 target waveforms
+    xh = torch.empty(B, 2, T, dtype=torch.float32).pin_memory()
+    xh.copy_(x.view(B, 2, T).cpu())
+    yh = torch.empty(N_TARGETS, B, 2, T, dtype=torch.float32).pin_memory()
+    gains = torch.tensor(GAINS, device=dev).view(4, 1, 1, 1, 1, 1, 1)
+
+    def step_e2e():
+        xd = xh.to(dev, non_blocking=True)
+        X = nsgt(xd)
+        Yl = [Xb.unsqueeze(0) * gains for Xb in X]          # [4,B,2,F,S,M,2] stand-in for Unmix output
+        y = insgt(Yl, T)
+        yh.copy_(y, non_blocking=True)
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for _ in range(e_steps):
+        step_e2e()
+    eb.record(stream)
+    barrier()
+    wall = (time.perf_counter() - t0) / e_steps
+    e_ms = max(ea.elapsed_time(eb) / e_steps, wall * 1e3)
+    te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_ms = float(te.item())
+    e2e = {"value": audio_s / (e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e_ms,
+           "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4),
+           "includes": "pinned H2D, NSGT_SL, 4-target gain stand-in (torch), INSGT_SL, pinned D2H"}
+
+    # ---- quality guard: the timed path really reconstructs (gain g of target t times the mixture)
+    err = float((yout[:rows_f] - GAINS[0] * x).abs().max())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, cores, sample = cpu_reference_arm(3, 1, args.cpu_sample_seconds)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample,
+               "ms_per_sample": dt * 1e3}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "sliCQT fwd+inv audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "max_abs_err_target0": err,
+        }))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+"""GPU tier (-m gpu): the sm_100a kernels, called through the C-ABI / the drop-in wrappers,
+against the oracle, the reference-generated golden vectors and size-independent properties."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle.slicq_oracle import SlicqOracle, snr_db
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5        # north star: max relative coefficient error
+SNR_SLACK_DB = 0.1    # north star: round-trip SNR within 0.1 dB of the reference
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tier needs CUDA"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def base(dev):
+    from xumx_slicq_b200 import NSGTBase
+    return NSGTBase("bark", 262, 32.9, device=dev)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return SlicqOracle(**common.BARK)
+
+
+def rel_err(c, r):
+    return float(np.abs(c - r).max() / np.abs(r).max())
+
+
+def test_native_library_is_loaded(base):
+    from xumx_slicq_b200 import _cabi
+    assert os.path.basename(_cabi.library_path()) == "libslicq.so"
+    with open("/proc/self/maps") as f:
+        base.nsgt.plan()  # forces the load
+        assert "libslicq.so" in f.read() or "libslicq.so" in open("/proc/self/maps").read()
+
+
+def test_forward_vs_reference_golden(base, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    buckets = [tuple(int(v) for v in b) for b in gold["buckets"]]
+    x = torch.from_numpy(common.small_input()).to(dev)
+    C = base.nsgt.forward((x,))
+    ref = common.unpack(gold["coefs"], buckets)
+    worst = max(rel_err(c.cpu().numpy(), r) for c, r in zip(C, ref))
+    assert worst < REL_TOL, worst
+
+
+def test_inverse_vs_reference_golden(base, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    buckets = [tuple(int(v) for v in b) for b in gold["buckets"]]
+    ref = common.unpack(gold["coefs"], buckets)
+    T = common.SMALL_T
+    y = base.nsgt.backward([torch.from_numpy(np.ascontiguousarray(r)).to(dev) for r in ref], T).cpu().numpy()
+    np.testing.assert_allclose(y, gold["y_roundtrip"], atol=5e-6)
+    P = common.perturb(ref)       # non-range ("model output like") coefficients
+    yp = base.nsgt.backward([torch.from_numpy(p).to(dev) for p in P], T).cpu().numpy()
+    np.testing.assert_allclose(yp, gold["y_perturbed"], atol=5e-6)
+    assert snr_db(gold["y_perturbed"], yp) > 120.0
+
+
+def test_forward_vs_oracle_float64(base, dev, orc):
+    x = common.small_input()
+    C = base.nsgt.forward((torch.from_numpy(x).to(dev),))
+    O = orc.forward(x.astype(np.float64))
+    worst = max(rel_err(c.cpu().numpy(), o) for c, o in zip(C, O))
+    assert worst < REL_TOL, worst
+
+
+def test_gspi_config1(base, dev, golden_dir):
+    """BASELINE.json configs[0]: gspi.wav round trip with the pretrained Bark parameters."""
+    gold = np.load(os.path.join(golden_dir, "gspi.npz"))
+    x = (gold["wav_int16"].astype(np.float32) / 32768.0)[None, :]
+    xt = torch.from_numpy(x).to(dev)
+    C = base.nsgt.forward((xt,))
+    assert C[0].shape[0] == int(gold["S"]) == 31
+    flat = np.concatenate([c.cpu().numpy().reshape(31, 1, -1) for c in C], axis=-1).reshape(-1)[::61]
+    assert np.abs(flat - gold["coef_sample"]).max() / float(gold["bucket_max"].max()) < REL_TOL
+    y = base.nsgt.backward(C, x.shape[-1]).cpu().numpy()
+    np.testing.assert_allclose(y.reshape(-1)[::7], gold["y_sample"], atol=5e-6)
+    ours = snr_db(x, y)
+    assert ours > float(gold["snr_db"]) - SNR_SLACK_DB, (ours, float(gold["snr_db"]))
+
+
+def test_edge_lengths(base, dev, golden_dir):
+    edge = np.load(os.path.join(golden_dir, "edge_lengths.npz"))
+    for T in (1, 4515, 9030, 9031, 13545, 18060, 18061):
+        xe = (np.random.RandomState(T).rand(1, T).astype(np.float32) * 2 - 1)
+        C = base.nsgt.forward((torch.from_numpy(xe).to(dev),))
+        assert C[0].shape[0] == int(edge[f"S_{T}"])
+        E = np.asarray([float((c.abs() ** 2).sum()) for c in C])
+        np.testing.assert_allclose(E, edge[f"E_{T}"], rtol=1e-4, atol=1e-9)
+        y = base.nsgt.backward(C, T).cpu().numpy()
+        np.testing.assert_allclose(y, edge[f"y_{T}"], atol=5e-6)
+
+
+def test_wrappers_dropin_contract(base, dev, orc, golden_dir):
+    from xumx_slicq_b200 import make_filterbanks, ComplexNorm
+    gold = np.load(os.path.join(golden_dir, "small_fwdinv.npz"))
+    nsgt, insgt = make_filterbanks(base)
+    x = torch.from_numpy(common.small_input()).view(1, 2, -1).to(dev)
+    X = nsgt(x)
+    assert [list(t.shape) for t in X] == gold["wrapper_shapes"].tolist()
+    assert all(t.dtype == torch.float32 and t.is_cuda for t in X)
+    mags = ComplexNorm()(X)
+    assert mags[5].shape == X[5].shape[:-1]
+    y = insgt(X, x.shape[-1])
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert snr_db(x.cpu().numpy(), y.cpu().numpy()) > 130.0
+    # 7-D (targets first) input as Separator.forward passes it (separator.py:174)
+    Y4 = [torch.stack([t * s for s in (1.0, 0.5, 0.25, 0.125)]) for t in X]
+    y4 = insgt(Y4, x.shape[-1])
+    assert y4.shape == (4, 1, 2, x.shape[-1])
+    np.testing.assert_allclose(y4[3].cpu().numpy(), 0.125 * y.cpu().numpy(), atol=2e-6)
+    # CPU input to a CUDA module (predict_input_size, transforms.py:83-89)
+    Xs, xs = base.predict_input_size(1, 2, 0.5)
+    assert xs.device.type == "cpu" and Xs[0].is_cuda and Xs[0].shape[:2] == (1, 2)
+    # 4-D input [4,B,2,T] -> 7-D output (training.py:81)
+    X4 = nsgt(torch.rand(4, 1, 2, 20000, device=dev))
+    assert X4[1].dim() == 7 and X4[1].shape[:3] == (4, 1, 2)
+    # float64 input -> float32 output
+    assert nsgt(x.double())[0].dtype == torch.float32
+    # deepcopy / .to() plumbing (training.py:118,356)
+    b2 = copy.deepcopy(base).to(dev)
+    X2 = make_filterbanks(b2)[0](x)
+    assert all(torch.equal(a, b) for a, b in zip(X, X2))
+
+
+def test_full_size_30s_stereo_properties(base, dev):
+    """BASELINE.json configs[1] size (30 s stereo, S=148): round trip, linearity, determinism."""
+    g = torch.Generator(device=dev).manual_seed(0)
+    T = 1323000
+    x = torch.rand(2, T, device=dev, generator=g) * 2 - 1
+    z = torch.rand(2, T, device=dev, generator=g) * 2 - 1
+    nsg = base.nsgt
+    Cx = nsg.forward_rows(x)
+    assert Cx[0].shape == (2, 1, 148, 28)
+    y = nsg.backward_rows(Cx, T)
+    snr = snr_db(x.cpu().numpy(), y.cpu().numpy())
+    assert snr > 131.4 - SNR_SLACK_DB, snr          # reference fp32: 131.48 dB at this size
+    assert float((y - x).abs().max()) < 2e-6
+    # determinism: bitwise identical on a second run
+    assert all(torch.equal(a, b) for a, b in zip(Cx, nsg.forward_rows(x)))
+    assert torch.equal(y, nsg.backward_rows(Cx, T))
+    # linearity of analysis and synthesis
+    Cz = nsg.forward_rows(z)
+    Cs = nsg.forward_rows(0.5 * x - 0.25 * z)
+    for a, b, c in zip(Cx, Cz, Cs):
+        ref = 0.5 * a - 0.25 * b
+        assert float((c - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-7
+    ys = nsg.backward_rows([0.5 * a - 0.25 * b for a, b in zip(Cx, Cz)], T)
+    assert float((ys - (0.5 * x - 0.25 * z)).abs().max()) < 4e-6
+
+
+def test_training_shape_batch(base, dev):
+    """BASELINE.json configs[2]: batch of 64 stereo 2 s excerpts (N=128 rows, S=11)."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.rand(64, 2, 88200, device=dev, generator=g) * 2 - 1
+    X = nsgt(x)
+    assert X[1].shape == (64, 2, 86, 11, 16, 2)
+    y = insgt(X, 88200)
+    assert snr_db(x.cpu().numpy(), y.cpu().numpy()) > 131.6 - SNR_SLACK_DB
+    # rows are independent: row 77 alone gives the same bits
+    X1 = nsgt(x[38:39, 1:2])
+    for a, b in zip(X, X1):
+        assert torch.equal(a[38, 1], b[0, 0])
+
+
+def test_chunking_is_invisible(dev):
+    """Chunks only bound the L2-resident scratch: results must not depend on the chunk size."""
+    from xumx_slicq_b200 import NSGTBase
+    T = 40 * 9030
+    x = torch.rand(3, T, device=dev) * 2 - 1
+    outs = []
+    for mb in ("1", "3", "64"):
+        os.environ["SLICQ_CHUNK_MB"] = mb
+        try:
+            b = NSGTBase("bark", 262, 32.9, device=dev)
+            C = b.nsgt.forward_rows(x)
+            outs.append((C, b.nsgt.backward_rows(C, T)))
+        finally:
+            os.environ.pop("SLICQ_CHUNK_MB", None)
+    for C, y in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(C, outs[0][0]))
+        assert torch.equal(y, outs[0][1])
+
+
+def test_slice_range_sharding_bitwise(base, dev):
+    """BASELINE.json configs[3] on one GPU with virtual ranks: slices split into contiguous ranges,
+    one half-slice halo per boundary, result bitwise equal to the unsharded transform."""
+    nsg = base.nsgt
+    hop = nsg.sl_len // 2
+    T = 7938000 // 6   # 30 s of the 3-min track is enough to cover every boundary case quickly
+    x = torch.rand(2, T, device=dev) * 2 - 1
+    S = nsg.n_slices(T)
+    full = nsg.forward_rows(x)
+    y_full = nsg.backward_rows(full, T)
+    for world in (2, 4, 8):
+        cuts = [round(i * S / world) for i in range(world + 1)]
+        ys, halos = [], []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo, hi = max(0, (a - 1) * hop), min(T, b * hop)
+            part = nsg.forward_rows(x[:, lo:hi].contiguous(), k0=a, n_slices=b - a, t0=lo)
+            assert all(torch.equal(pc, fc[:, :, a:b]) for pc, fc in zip(part, full))
+            halo = torch.zeros(2, hop, device=dev)
+            ys.append(nsg.backward_rows(part, min(T, b * hop) - a * hop, k0=a, t0=a * hop, halo_out=halo))
+            halos.append(halo)
+        for i in range(world - 1):
+            ys[i][:, -hop:] += halos[i + 1]
+        assert torch.equal(torch.cat(ys, dim=1), y_full), world
+
+
+def test_error_paths(base, dev):
+    from xumx_slicq_b200 import make_filterbanks, NSGTBase
+    with pytest.raises(ValueError):
+        make_filterbanks(base, sample_rate=48000.0)
+    with pytest.raises(ValueError):
+        base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64, device=dev)], 100)
+    with pytest.raises(ValueError):      # a Bark configuration whose slice length has no compiled kernel
+        NSGTBase("bark", 100, 50.0, device=dev).nsgt.plan()

@@ -24,7 +24,9 @@ EXPORTS = (
     "slicq_abi_version", "slicq_last_error", "slicq_plan_create", "slicq_plan_destroy",
     "slicq_plan_n_buckets", "slicq_plan_bucket_info", "slicq_plan_num_slices",
     "slicq_scratch_bytes", "slicq_forward", "slicq_inverse", "slicq_launch_count",
+    "slicq_profile_enable", "slicq_profile_read",
 )
+KERNEL_NAMES = ("slice_fft_fwd", "bins_fwd", "bins_inv", "slice_fft_inv", "overlap_add")
 
 
 class SlicqTablesC(C.Structure):
@@ -72,7 +74,23 @@ def _declare(lib: C.CDLL) -> C.CDLL:
                                   C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.slicq_inverse.restype = C.c_int
     lib.slicq_launch_count.restype = C.c_int64
+    lib.slicq_profile_enable.argtypes = [C.c_int]
+    lib.slicq_profile_enable.restype = C.c_int
+    lib.slicq_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.slicq_profile_read.restype = C.c_int
     return lib
+
+
+def profile_enable(on: bool, lib: C.CDLL | None = None) -> None:
+    (lib or load()).slicq_profile_enable(int(bool(on)))
+
+
+def profile_read(lib: C.CDLL | None = None) -> dict:
+    """{kernel name: (total ms, launches)} since the last read (synchronises the recorded events)."""
+    ms = (C.c_double * 5)()
+    n = (C.c_int64 * 5)()
+    (lib or load()).slicq_profile_read(ms, n)
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_NAMES)}
 
 
 def library_path() -> str:

@@ -31,6 +31,27 @@ namespace {
 thread_local std::string g_err;
 long long g_launches = 0;
 
+// ---- optional per-kernel CUDA-event timing (bench.py roofline accounting) -----------------
+enum { K_SLICE_FWD = 0, K_BINS_FWD, K_BINS_INV, K_SLICE_INV, K_OLA, K_COUNT };
+bool g_prof = false;
+#ifndef SLICQ_EMU
+struct ProfRec { int kid; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof_recs;
+#endif
+struct ProfScope {
+#ifndef SLICQ_EMU
+    int kid; cudaStream_t s; cudaEvent_t a, b; bool on;
+    ProfScope(int k, cudaStream_t st) : kid(k), s(st), on(g_prof) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, s); ProfRec r; r.kid = kid; r.a = a; r.b = b; g_prof_recs.push_back(r); }
+    }
+#else
+    ProfScope(int, cudaStream_t) {}
+#endif
+};
+
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -90,6 +111,24 @@ struct slicq_plan {
 extern "C" int slicq_abi_version(void) { return SLICQ_ABI_VERSION; }
 extern "C" const char* slicq_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t slicq_launch_count(void) { return g_launches; }
+
+extern "C" int slicq_profile_enable(int on) { g_prof = on != 0; return SLICQ_OK; }
+
+extern "C" int slicq_profile_read(double* ms, int64_t* launches) {
+    for (int i = 0; i < K_COUNT; ++i) { if (ms) ms[i] = 0.0; if (launches) launches[i] = 0; }
+#ifndef SLICQ_EMU
+    for (ProfRec& r : g_prof_recs) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            if (ms) ms[r.kid] += t;
+            if (launches) launches[r.kid] += 1;
+        }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+#endif
+    return SLICQ_OK;
+}
 
 extern "C" void slicq_plan_destroy(slicq_plan* p) {
     if (!p) return;
@@ -308,12 +347,12 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
     for (long long u0 = 0; u0 < units && rc == 0; u0 += cu) {
         const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
         sp.n_rs = n; sp.rs0 = (int)u0;
-        rc = slicq_launch_slice_fwd(&sp, s);
+        { ProfScope ps(K_SLICE_FWD, s); rc = slicq_launch_slice_fwd(&sp, s); }
         ++g_launches;
         if (rc) break;
         bp->n_rs = n; bp->rs0 = (int)u0;
         const int tiles = fill_bins_params(p, buckets, *bp, n);
-        rc = slicq_launch_bins(bp, tiles, p->bins_smem, 0, s);
+        { ProfScope ps(K_BINS_FWD, s); rc = slicq_launch_bins(bp, tiles, p->bins_smem, 0, s); }
         ++g_launches;
     }
     delete bp;
@@ -355,15 +394,15 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
         const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
         bp->n_rs = n; bp->rs0 = (int)u0;
         const int tiles = fill_bins_params(p, buckets, *bp, n);
-        rc = slicq_launch_bins(bp, tiles, p->bins_smem, 1, s);
+        { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, tiles, p->bins_smem, 1, s); }
         ++g_launches;
         if (rc) break;
         sp.n_rs = n; sp.rs0 = (int)u0;
-        rc = slicq_launch_slice_inv(&sp, s);
+        { ProfScope ps(K_SLICE_INV, s); rc = slicq_launch_slice_inv(&sp, s); }
         ++g_launches;
         if (rc) break;
         op.n_rs = n; op.rs0 = (int)u0;
-        rc = slicq_launch_ola(&op, s);
+        { ProfScope ps(K_OLA, s); rc = slicq_launch_ola(&op, s); }
         ++g_launches;
     }
     delete bp;
