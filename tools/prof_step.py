@@ -18,8 +18,10 @@ x = torch.rand(2 * a.batch, T, device=dev) * 2 - 1
 C = nsg.forward_rows(x)
 Y = [torch.cat([c * g for g in (0.9, 0.6, 0.4, 0.2)], dim=0).contiguous() for c in C]
 torch.cuda.synchronize()
+torch.cuda.profiler.start()   # use with: ncu --profile-from-start off
 for _ in range(a.steps):
     C = nsg.forward_rows(x)
     y = nsg.backward_rows(Y, T)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done", float((y[: 2 * a.batch] - 0.9 * x).abs().max()))

@@ -94,7 +94,8 @@ def profile_read(lib: C.CDLL | None = None) -> dict:
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, LIB_NAME)
+    # SLICQ_B200_LIB selects another *build of the same CUDA library* (kernel tuning sweeps)
+    return os.environ.get("SLICQ_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
 
 _lib = None

@@ -6,7 +6,8 @@
 // with the Good-Thomas prime-factor algorithm on the 3-D index space 43 x 15 x 14: the three
 // factors are pairwise coprime, so there are NO twiddle multiplications between the passes --
 // input index n lives at (n mod 43, n mod 15, n mod 14), output index
-// k = (210 k1 + 602 k2 + 645 k3) mod 9030 lives at (k1, k2, k3).
+// k = (210 k1 + 602 k2 + 645 k3) mod 9030 lives at (k1, k2, k3).  Both maps are precomputed
+// (perm_in / perm_out, 18 KB each, L1/L2 resident) so the kernels do no modular arithmetic.
 //   pass A  43-point symmetric real half-transforms down the first axis (rdft_sym<43>), the real
 //           and the imaginary part of a column on separate threads, in place
 //   pass B  combine (A_k -/+ i B_k) fused with the 15-point codelet, rows k1 and 43-k1 together
@@ -14,10 +15,18 @@
 // followed (forward) / preceded (inverse) by the even/odd split that turns the N-point complex
 // transform into the L-point real one.
 //
+// Shared-memory layout: element (a, b, c) at a*SA + b*SB + c (float2 units) with SB = 15 and
+// SA = 227: SA odd makes the "lane <-> a" task orders of passes B and C conflict-free for 64-bit
+// accesses, and SA + SB + 1 odd does the same for the permuted load / store phases.
+//
 // reference: nsgt/slicing.py:7-72 + nsgt/nsgtf.py:40 (forward), nsgt/nsigtf.py:93-103 +
 //            nsgt/unslicing.py:33-69 + nsgt/slicq.py:207-230 (inverse); closed forms in DESIGN.md.
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
+
+#ifndef SLICQ_SLICE_THREADS
+#define SLICQ_SLICE_THREADS 256
+#endif
 
 namespace {
 
@@ -32,23 +41,19 @@ template <int P1_, int P2_, int P3_>
 struct Pfa3 {
     static constexpr int P1 = P1_, P2 = P2_, P3 = P3_;
     static constexpr int N = P1 * P2 * P3;
-    static constexpr int SB = P3 + 1;  // pitch of axis 2 (float2): odd -> conflict-free pass C
-    static constexpr int SA_MIN = P2 * SB;
-    // pitch of axis 1: == 14 (mod 16) keeps the (k1, n3) task order of pass B conflict-free
-    static constexpr int SA = SA_MIN + ((14 - SA_MIN % 16) + 16) % 16;
+    static constexpr int SB = (P3 % 2 == 0) ? P3 + 1 : P3 + 2;              // odd
+    static constexpr int SA = (P2 * SB) % 2 == 1 ? P2 * SB + 2 : P2 * SB + 1;  // odd, > P2*SB
     static constexpr int SMEM_ELEMS = P1 * SA;
     static constexpr int I1 = cmodinv(N / P1, P1), I2 = cmodinv(N / P2, P2), I3 = cmodinv(N / P3, P3);
-    static SLICQ_DEVFN int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
-    static SLICQ_DEVFN int pos_out(int k) {
-        return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3);
-    }
+    static int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
+    static int pos_out(int k) { return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3); }
 };
 
 template <class PF, bool INV>
 SLICQ_DEVFN void pfa_passes(float2* Z) {
     constexpr int P1 = PF::P1, P2 = PF::P2, P3 = PF::P3, SA = PF::SA, SB = PF::SB;
     float* Zf = reinterpret_cast<float*>(Z);
-    // ---- pass A
+    // ---- pass A: lane <-> (column, re|im): consecutive words of one row
     for (int t = threadIdx.x; t < P2 * P3 * 2; t += blockDim.x) {
         const int c2 = t & 1, col = t >> 1;
         const int b = col / P3, c = col - b * P3;
@@ -59,10 +64,10 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
         rdft_sym<P1>(x, base, SA * 2);
     }
     __syncthreads();
-    // ---- pass B
+    // ---- pass B: lane <-> kk (row pair), pitch SA odd
     constexpr int H1 = (P1 - 1) / 2;
     for (int t = threadIdx.x; t < (H1 + 1) * P3; t += blockDim.x) {
-        const int kk = t / P3, c = t - kk * P3;
+        const int c = t / (H1 + 1), kk = t - c * (H1 + 1);
         float2* rp = Z + kk * SA + c;
         float2* rm = Z + (P1 - kk) * SA + c;
         float2 xp[P2], xm[P2];
@@ -92,9 +97,9 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
         }
     }
     __syncthreads();
-    // ---- pass C
+    // ---- pass C: lane <-> a, pitch SA odd
     for (int t = threadIdx.x; t < P1 * P2; t += blockDim.x) {
-        const int a = t / P2, b = t - a * P2;
+        const int b = t / P1, a = t - b * P1;
         float2* r = Z + a * SA + b * SB;
         float2 v[P3];
 #pragma unroll
@@ -106,19 +111,12 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
     __syncthreads();
 }
 
-// sum of the windowed bin spectra covering position f (fixed bin order -> deterministic)
-SLICQ_DEVFN float2 gather_spectrum(const SlicqDeviceTables& t, const float2* __restrict__ row, int f) {
-    const int j0 = t.jlo[f];
-    const int cnt = t.jcnt[f];
-    float2 acc = make_float2(0.f, 0.f);
-    for (int j = j0; j < j0 + cnt; ++j) {
-        const int M = __ldg(t.bin_M + j);
-        int d = f - __ldg(t.bin_pos + j);
-        if (d < 0) d += M;
-        const float2 v = row[__ldg(t.bin_coff + j) + d];
-        acc.x += v.x;
-        acc.y += v.y;
-    }
+// sum of the windowed bin spectra covering one position (fixed bin order -> deterministic)
+SLICQ_DEVFN float2 gather_spectrum(const int4 o, const float2* __restrict__ row) {
+    float2 acc = row[o.x];
+    if (o.y >= 0) { const float2 v = row[o.y]; acc.x += v.x; acc.y += v.y; }
+    if (o.z >= 0) { const float2 v = row[o.z]; acc.x += v.x; acc.y += v.y; }
+    if (o.w >= 0) { const float2 v = row[o.w]; acc.x += v.x; acc.y += v.y; }
     return acc;
 }
 
@@ -127,9 +125,9 @@ SLICQ_DEVFN float2 gather_spectrum(const SlicqDeviceTables& t, const float2* __r
 typedef Pfa3<43, 15, 14> Pfa9030;
 
 // ------------------------------------------------------------------------------------------
-// stage 1: one CTA per (row, slice).  x -> H (half spectrum, N+1 complex bins)
+// stage 1: one CTA per (row, slice).  x -> padded half spectrum H_ext[pad_l + f], f in [-pad_l, N + pad_r]
 template <class PF>
-__global__ void __launch_bounds__(256, 2) slice_fft_fwd_kernel(const __grid_constant__ SlicqSliceParams p) {
+__global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
     constexpr int N = PF::N;
     const int rsl = blockIdx.x;
@@ -137,32 +135,80 @@ __global__ void __launch_bounds__(256, 2) slice_fft_fwd_kernel(const __grid_cons
     const int row = rs / p.S, k = rs - row * p.S;
     const long long s0 = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;  // x index of slice sample 0
     const float* __restrict__ xr = p.x + row * p.x_row_stride;
-    const float* __restrict__ tw = p.t.tukey;
-    for (int e = threadIdx.x; e < N; e += blockDim.x) {
-        const long long s = s0 + 2 * e;
-        const float w0 = __ldg(tw + 2 * e), w1 = __ldg(tw + 2 * e + 1);
-        float a = 0.f, b = 0.f;
-        if (w0 != 0.f && s >= 0 && s < p.T) a = __ldg(xr + s) * w0;
-        if (w1 != 0.f && s + 1 >= 0 && s + 1 < p.T) b = __ldg(xr + s + 1) * w1;
-        Z[PF::pos_in(e)] = make_float2(a, b);
+    const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
+    const unsigned short* __restrict__ pin = p.t.perm_in;
+    const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;
+    // zero part of the window: no loads
+    for (int e = threadIdx.x; e < N - (e_hi - e_lo); e += blockDim.x) {
+        const int ee = e < e_lo ? e : e + (e_hi - e_lo);
+        Z[__ldg(pin + ee)] = make_float2(0.f, 0.f);
+    }
+    const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;   // x range touched by the window support
+    const bool interior = sa >= 0 && sb <= p.T;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
+    constexpr int U = 4;   // loads in flight per thread
+    if (interior && vec) {
+        const float2* __restrict__ x2 = reinterpret_cast<const float2*>(xr + s0);
+        for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += U * blockDim.x) {
+            float2 v[U], w[U];
+            int pi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < e_hi) { pi[u] = __ldg(pin + e); w[u] = __ldg(tw2 + e); v[u] = __ldg(x2 + e); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < e_hi) Z[pi[u]] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
+            }
+        }
+    } else {
+        for (int e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+            const long long s = s0 + 2 * e;
+            const float2 w = __ldg(tw2 + e);
+            float a = 0.f, b = 0.f;
+            if (s >= 0 && s < p.T) a = __ldg(xr + s) * w.x;
+            if (s + 1 >= 0 && s + 1 < p.T) b = __ldg(xr + s + 1) * w.y;
+            Z[__ldg(pin + e)] = make_float2(a, b);
+        }
     }
     __syncthreads();
     pfa_passes<PF, false>(Z);
-    // even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O)
-    float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride;
-    for (int kk = threadIdx.x; kk <= N / 2; kk += blockDim.x) {
-        const float2 zk = Z[PF::pos_out(kk)];
-        if (kk == 0) {
-            H[0] = make_float2(zk.x + zk.y, 0.f);
-            H[N] = make_float2(zk.x - zk.y, 0.f);
-        } else {
-            const float2 zn = Z[PF::pos_out(N - kk)];
-            const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-            // O = -(i/2) (zk - conj(zn))
-            const float2 O = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-            const float2 t = cmul(__ldg(p.t.post_tw + kk), O);
-            H[kk] = make_float2(E.x + t.x, E.y + t.y);
-            H[N - kk] = make_float2(E.x - t.x, -(E.y - t.y));
+    // even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O); mirrored margins for the bins
+    // that reach below DC / above Nyquist (Hermitian symmetry of a real slice)
+    float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
+    const unsigned short* __restrict__ pout = p.t.perm_out;
+    const int pad_l = p.t.pad_l, pad_r = p.t.pad_r;
+    constexpr int UP = 4;
+    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UP * blockDim.x) {
+        int pk[UP], pn[UP];
+        float2 wk[UP];
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+            const int kk = kk0 + u * blockDim.x;
+            if (kk <= N / 2) { pk[u] = __ldg(pout + kk); pn[u] = __ldg(pout + N - kk); wk[u] = __ldg(p.t.post_tw + kk); }
+        }
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+            const int kk = kk0 + u * blockDim.x;
+            if (kk > N / 2) continue;
+            const float2 zk = Z[pk[u]];
+            if (kk == 0) {
+                H[0] = make_float2(zk.x + zk.y, 0.f);
+                H[N] = make_float2(zk.x - zk.y, 0.f);
+            } else {
+                const float2 zn = Z[pn[u]];
+                const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                const float2 O = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));  // -(i/2)(zk - conj zn)
+                const float2 t = cmul(wk[u], O);
+                const float2 hk = make_float2(E.x + t.x, E.y + t.y);
+                const float2 hn = make_float2(E.x - t.x, -(E.y - t.y));
+                H[kk] = hk;
+                H[N - kk] = hn;
+                if (kk <= pad_l) H[-kk] = make_float2(hk.x, -hk.y);
+                if (kk <= pad_r) H[N + kk] = make_float2(hn.x, -hn.y);
+            }
         }
     }
 }
@@ -170,32 +216,62 @@ __global__ void __launch_bounds__(256, 2) slice_fft_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------
 // stage 3b: one CTA per (row, slice).  packed windowed bin spectra T -> slice signal u [L]
 template <class PF>
-__global__ void __launch_bounds__(256, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
+__global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
     constexpr int N = PF::N;
     const int rsl = blockIdx.x;
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
-    for (int kk = threadIdx.x; kk <= N / 2; kk += blockDim.x) {
-        const float2 rk = gather_spectrum(p.t, Trow, kk);
-        const float2 rn = gather_spectrum(p.t, Trow, N - kk);
-        if (kk == 0) {
-            // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
-            Z[PF::pos_in(0)] = make_float2(rk.x + rn.x, rk.x - rn.x);
-        } else {
-            const float2 E = make_float2(rk.x + rn.x, rk.y - rn.y);   // rk + conj(rn)
-            const float2 O = make_float2(rk.x - rn.x, rk.y + rn.y);   // rk - conj(rn)
-            const float2 t = cmul_conj(O, __ldg(p.t.post_tw + kk));   // conj(w^k) O
-            Z[PF::pos_in(kk)] = make_float2(E.x - t.y, E.y + t.x);       // E + i t
-            Z[PF::pos_in(N - kk)] = make_float2(E.x + t.y, t.x - E.y);   // conj(E - i t)
+    const unsigned short* __restrict__ pin = p.t.perm_in;
+    constexpr int UG = 2;
+    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UG * blockDim.x) {
+        int4 ok[UG], on[UG];
+        int pk[UG], pn[UG];
+        float2 wk[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int kk = kk0 + u * blockDim.x;
+            if (kk <= N / 2) {
+                ok[u] = __ldg(p.t.goff + kk); on[u] = __ldg(p.t.goff + N - kk);
+                pk[u] = __ldg(pin + kk); pn[u] = __ldg(pin + (kk == 0 ? 0 : N - kk)); wk[u] = __ldg(p.t.post_tw + kk);
+            }
+        }
+        float2 rk[UG], rn[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int kk = kk0 + u * blockDim.x;
+            if (kk <= N / 2) { rk[u] = gather_spectrum(ok[u], Trow); rn[u] = gather_spectrum(on[u], Trow); }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int kk = kk0 + u * blockDim.x;
+            if (kk > N / 2) continue;
+            if (kk == 0) {
+                // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
+                Z[pk[u]] = make_float2(rk[u].x + rn[u].x, rk[u].x - rn[u].x);
+            } else {
+                const float2 E = make_float2(rk[u].x + rn[u].x, rk[u].y - rn[u].y);   // rk + conj(rn)
+                const float2 O = make_float2(rk[u].x - rn[u].x, rk[u].y + rn[u].y);   // rk - conj(rn)
+                const float2 t = cmul_conj(O, wk[u]);                                 // conj(w^k) O
+                Z[pk[u]] = make_float2(E.x - t.y, E.y + t.x);       // E + i t
+                Z[pn[u]] = make_float2(E.x + t.y, t.x - E.y);       // conj(E - i t)
+            }
         }
     }
     __syncthreads();
     pfa_passes<PF, true>(Z);
     const float scale = 1.0f / (float)(2 * N);
     float2* __restrict__ U = reinterpret_cast<float2*>(p.u + (long long)rsl * (2 * N));
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const float2 z = Z[PF::pos_out(n)];
-        U[n] = make_float2(z.x * scale, z.y * scale);
+    const unsigned short* __restrict__ pout = p.t.perm_out;
+    constexpr int UO = 4;
+    for (int n0 = threadIdx.x; n0 < N; n0 += UO * blockDim.x) {
+        int po[UO];
+#pragma unroll
+        for (int u = 0; u < UO; ++u) if (n0 + u * blockDim.x < N) po[u] = __ldg(pout + n0 + u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < UO; ++u) {
+            const int n = n0 + u * blockDim.x;
+            if (n < N) { const float2 z = Z[po[u]]; U[n] = make_float2(z.x * scale, z.y * scale); }
+        }
     }
 }
 
@@ -203,20 +279,21 @@ __global__ void __launch_bounds__(256, 2) slice_fft_inv_kernel(const __grid_cons
 // stage 4: overlap-add of the chunk's slices into y.
 //   out hop h (samples [h*hop, (h+1)*hop) of the padded signal) = second half of slice h
 //                                                                + first half of slice h+1.
-//   grid.x = n_rs units, grid.y = 2: y==0 -> "store" job of unit (its hop), y==1 -> "carry"
-//   job (first half of the chunk's first slice of a row, whose partner was written earlier).
+//   grid = (units, pieces, 2): z==0 -> "store" job of the unit's own hop, z==1 -> "carry" job
+//   (first half of a slice whose left neighbour was written by an earlier launch / other shard).
 __global__ void __launch_bounds__(256) overlap_add_kernel(const __grid_constant__ SlicqOlaParams p) {
     const int rsl = blockIdx.x;
     const int rs = p.rs0 + rsl;
     const int row = rs / p.S, k = rs - row * p.S;
     const float* __restrict__ u = p.u + (long long)rsl * p.L;
     float* __restrict__ yr = p.y + row * p.y_row_stride;
-    if (blockIdx.y == 0) {
-        // hop h = k: u_k[hop + q] (+ u_{k+1}[q] when that slice is in this chunk)
+    const int q_lo = (int)(((long long)p.hop * blockIdx.y) / p.pieces);
+    const int q_hi = (int)(((long long)p.hop * (blockIdx.y + 1)) / p.pieces);
+    if (blockIdx.z == 0) {
         const bool has_next = (k + 1 < p.S) && (rsl + 1 < p.n_rs);
         const float* __restrict__ un = u + p.L;
         const long long tb = (p.k0 + k) * (long long)p.hop - p.t0;
-        for (int q = threadIdx.x; q < p.hop; q += blockDim.x) {
+        for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) {
             const long long t = tb + q;
             if (t < 0 || t >= p.length) continue;
             float v = u[p.hop + q];
@@ -230,11 +307,11 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(const __grid_constant_
         if (k == 0) {
             if (p.halo_out == nullptr || p.k0 == 0) return;  // hop -1 of the whole signal: dropped
             float* __restrict__ h = p.halo_out + (long long)row * p.hop;
-            for (int q = threadIdx.x; q < p.hop; q += blockDim.x) h[q] = u[q];
+            for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) h[q] = u[q];
             return;
         }
         const long long tb = (p.k0 + k - 1) * (long long)p.hop - p.t0;
-        for (int q = threadIdx.x; q < p.hop; q += blockDim.x) {
+        for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) {
             const long long t = tb + q;
             if (t < 0 || t >= p.length) continue;
             yr[t] += u[q];
@@ -242,10 +319,21 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(const __grid_constant_
     }
 }
 
-// host-side launchers -----------------------------------------------------------------------
+// host-side helpers / launchers ---------------------------------------------------------------
 extern "C" int slicq_slice_smem_bytes(int L) {
     if (L == 2 * Pfa9030::N) return (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     return -1;
+}
+
+// fills perm_in[N] and perm_out[N+1] for slice length L (host)
+extern "C" int slicq_slice_perm(int L, unsigned short* perm_in, unsigned short* perm_out) {
+    if (L != 2 * Pfa9030::N) return -1;
+    for (int n = 0; n < Pfa9030::N; ++n) {
+        perm_in[n] = (unsigned short)Pfa9030::pos_in(n);
+        perm_out[n] = (unsigned short)Pfa9030::pos_out(n);
+    }
+    perm_out[Pfa9030::N] = perm_out[0];
+    return 0;
 }
 
 extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s) {
@@ -254,7 +342,7 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
     const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     static int attr_done = 0;
     if (!attr_done) { SLICQ_SET_SMEM(slice_fft_fwd_kernel<Pfa9030>, smem); attr_done = 1; }
-    SLICQ_LAUNCH(slice_fft_fwd_kernel<Pfa9030>, dim3(p->n_rs), dim3(256), smem, s, *p);
+    SLICQ_LAUNCH(slice_fft_fwd_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
     return (int)cudaGetLastError();
 }
 
@@ -264,12 +352,12 @@ extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s)
     const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     static int attr_done = 0;
     if (!attr_done) { SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem); attr_done = 1; }
-    SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3(p->n_rs), dim3(256), smem, s, *p);
+    SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
     return (int)cudaGetLastError();
 }
 
 extern "C" int slicq_launch_ola(const SlicqOlaParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
-    SLICQ_LAUNCH(overlap_add_kernel, dim3(p->n_rs, 2), dim3(256), 0, s, *p);
+    SLICQ_LAUNCH(overlap_add_kernel, dim3(p->n_rs, p->pieces, 2), dim3(256), 0, s, *p);
     return (int)cudaGetLastError();
 }

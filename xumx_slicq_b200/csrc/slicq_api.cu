@@ -13,11 +13,40 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #ifdef SLICQ_EMU
-dim3 threadIdx, blockIdx, blockDim, gridDim;
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+thread_local dim3 threadIdx;
+dim3 blockIdx, blockDim, gridDim;
 static unsigned char slicq_emu_smem_buf[256 * 1024] __attribute__((aligned(16)));
 unsigned char* slicq_emu_smem = slicq_emu_smem_buf;
+namespace {
+struct EmuBarrier {
+    std::mutex m; std::condition_variable cv; int count = 0, gen = 0, n = 1;
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+} g_emu_bar;
+}  // namespace
+void slicq_emu_sync() { g_emu_bar.wait(); }
+void slicq_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+    gridDim = grid; blockDim = block; g_emu_bar.n = (int)block.x;
+    std::vector<std::thread> th(block.x);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx = dim3(bx, by, bz);
+                for (unsigned t = 0; t < block.x; ++t)
+                    th[t] = std::thread([t, &body]() { threadIdx = dim3(t, 0, 0); body(); });
+                for (unsigned t = 0; t < block.x; ++t) th[t].join();
+            }
+}
 #endif
 
 extern "C" int slicq_launch_bins(const SlicqBinsParams* p, int n_tiles, int smem_bytes, int synth, cudaStream_t s);
@@ -25,6 +54,8 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s);
 extern "C" int slicq_launch_ola(const SlicqOlaParams* p, cudaStream_t s);
 extern "C" int slicq_slice_smem_bytes(int L);
+extern "C" int slicq_bins_threads(void);
+extern "C" int slicq_slice_perm(int L, unsigned short* perm_in, unsigned short* perm_out);
 
 namespace {
 
@@ -70,9 +101,9 @@ const FftPlan* find_fft_plan(int M) {
     return nullptr;
 }
 
-// shared-memory bytes one transform of this plan needs in a tile (max over analysis / synthesis)
+// shared-memory bytes one transform of this plan needs (max over analysis / synthesis)
 int fft_smem_per_transform(const FftPlan& f) {
-    if (f.kind == 1) return 0;
+    if (f.kind == 1) return (f.M + 1) * 8;
     if (f.kind == 2) {
         const int bp = (f.B % 2 == 0) ? f.B + 1 : f.B;
         const int ap = (f.A % 2 == 0) ? f.A + 1 : f.A;
@@ -82,8 +113,16 @@ int fft_smem_per_transform(const FftPlan& f) {
     return f.M * 8;  // kind 3: R * 2 * P floats
 }
 
+// threads one transform occupies in the pass whose per-thread state is hoisted out of the unit loop
+int fft_threads_per_transform(const FftPlan& f) {
+    if (f.kind == 1) return 1;
+    if (f.kind == 2) return f.B;
+    return 2 * f.B;  // kind 3: (n2, re|im)
+}
+
 struct Bucket {
-    int M, first_bin, n_bins, G, tw_off, kind, A, B, smem_per_fft;
+    int M, first_bin, n_bins, gt, tw_off, kind, A, B, smem_per_fft;
+    double cost;     // relative work per unit (for the job split)
 };
 
 template <class T> int upload(const std::vector<T>& h, const T** d, std::vector<void*>& owned) {
@@ -104,8 +143,12 @@ struct slicq_plan {
     SlicqDeviceTables dev;
     std::vector<void*> owned;
     int bins_smem;        // dynamic shared memory of the bins kernels
+    int pad_l, pad_r;
     long long spec_stride_fwd;
     long long chunk_bytes;
+    int target_jobs;      // CTAs per bins launch the job split aims for
+    int min_iters;        // ... but a job keeps at least this many iterations (instruction-cache reuse)
+    int only_bucket;      // -1, or (SLICQ_ONLY_BUCKET, tuning aid) the single bucket the bins kernels process
 };
 
 extern "C" int slicq_abi_version(void) { return SLICQ_ABI_VERSION; }
@@ -187,7 +230,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         Bucket b;
         b.M = p->bin_M[j]; b.first_bin = j; b.n_bins = 1; b.tw_off = tw_off;
         b.kind = f->kind; b.A = f->A; b.B = f->B; b.smem_per_fft = fft_smem_per_transform(*f);
-        b.G = 1;
+        b.gt = 1; b.cost = 0.0;
         tw_off += b.M;
         p->buckets.push_back(b);
     }
@@ -195,28 +238,49 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         delete p;
         return fail(SLICQ_E_UNSUPPORTED, "too many buckets");
     }
-    // tile sizes: ~4096 coefficients per CTA, shared memory <= 64 KB
+    // units per CTA iteration: fill the 256 threads of the hoisted pass, shared memory <= 48 KB
     p->bins_smem = 0;
     for (Bucket& b : p->buckets) {
-        int G = 4096 / (b.n_bins * b.M);
-        if (G < 1) G = 1;
-        if (G > 16) G = 16;
-        while (G > 1 && b.n_bins * G * b.smem_per_fft > 64 * 1024) --G;
-        b.G = G;
-        const int sm = b.n_bins * G * b.smem_per_fft;
+        const FftPlan* f = find_fft_plan(b.M);
+        const int nthr = slicq_bins_threads();
+        int gt = nthr / (b.n_bins * fft_threads_per_transform(*f));
+        if (gt < 1) gt = 1;
+        while (gt > 1 && b.n_bins * gt * b.smem_per_fft > 48 * 1024) --gt;
+        if (b.n_bins * fft_threads_per_transform(*f) > nthr) {
+            delete p;
+            return fail(SLICQ_E_UNSUPPORTED, "bucket has too many bins for one CTA");
+        }
+        b.gt = gt;
+        const int sm = b.n_bins * gt * b.smem_per_fft + 2048;   // + SLICQ_SLOT_BYTES
         if (sm > p->bins_smem) p->bins_smem = sm;
+        // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
+        b.cost = (double)b.n_bins * b.M * (log2((double)b.M) + (f->kind == 3 ? 0.12 * f->A : 0.0) + 4.0);
     }
 
     // ---- derived tables
     std::vector<float> wf(p->sum_M), wi(p->sum_M), tuk(t->tukey, t->tukey + L);
+    int pad_l = 0, pad_r = 0;
     for (int j = 0; j < J; ++j) {
         const int M = p->bin_M[j], o = p->bin_coff[j];
         const double sgn = ((p->bin_pos[j] / 2) % 2) ? -1.0 : 1.0;
-        for (int m = 0; m < M; ++m) {
-            wf[o + m] = (float)((double)t->win_fwd[o + m] * sgn / (double)M);
-            wi[o + m] = (float)((double)t->win_inv[o + m] * sgn * (double)M);
+        for (int mc = 0; mc < M; ++mc) {            // centred order m' = m~ + M/2
+            const int m = (mc + M / 2) % M;         // reference order (peak at m = 0)
+            wf[o + mc] = (float)((double)t->win_fwd[o + m] * sgn / (double)M);
+            wi[o + mc] = (float)((double)t->win_inv[o + m] * sgn * (double)M);
         }
+        pad_l = std::max(pad_l, M / 2 - p->bin_pos[j]);
+        pad_r = std::max(pad_r, p->bin_pos[j] + M / 2 - 1 - p->N2);
     }
+    pad_l = (pad_l + 1) & ~1;
+    pad_r = (pad_r + 1) & ~1;
+    if (pad_l > p->N2 / 2 || pad_r > p->N2 / 2) {
+        delete p;
+        return fail(SLICQ_E_UNSUPPORTED, "bins reach too far beyond DC / Nyquist");
+    }
+    p->pad_l = pad_l; p->pad_r = pad_r;
+    int tw_lo = 0, tw_hi = L;
+    while (tw_lo < L && tuk[tw_lo] == 0.f) ++tw_lo;
+    while (tw_hi > tw_lo && tuk[tw_hi - 1] == 0.f) --tw_hi;
     std::vector<float2> post(p->N2 / 2 + 1), tw(tw_off);
     for (int k = 0; k <= p->N2 / 2; ++k) {
         const double a = -2.0 * M_PI * (double)k / (double)L;
@@ -227,25 +291,29 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
             const double a = -2.0 * M_PI * (double)j / (double)b.M;
             tw[b.tw_off + j] = make_float2((float)cos(a), (float)sin(a));
         }
-    std::vector<unsigned short> jlo(p->N2 + 1);
-    std::vector<unsigned char> jcnt(p->N2 + 1);
+    std::vector<int4> goff(p->N2 + 1);
     for (int f = 0; f <= p->N2; ++f) {
-        int first = -1, last = -1, n = 0;
+        int o[4] = {-1, -1, -1, -1}, n = 0;
         for (int j = 0; j < J; ++j) {
             const int d = f - p->bin_pos[j], h = p->bin_M[j] / 2;
-            if (d >= -h && d < h) { if (first < 0) first = j; last = j; ++n; }
+            if (d >= -h && d < h) {
+                if (n == 4) { delete p; return fail(SLICQ_E_UNSUPPORTED, "more than 4 bins overlap at one spectrum position"); }
+                o[n++] = p->bin_coff[j] + d + h;   // centred order
+            }
         }
-        if (n == 0 || last - first + 1 != n || n > 255) {
-            delete p;
-            return fail(SLICQ_E_UNSUPPORTED, "spectrum position not covered by a consecutive run of bins");
-        }
-        jlo[f] = (unsigned short)first;
-        jcnt[f] = (unsigned char)n;
+        if (n == 0) { delete p; return fail(SLICQ_E_UNSUPPORTED, "spectrum position not covered by any bin"); }
+        goff[f].x = o[0]; goff[f].y = o[1]; goff[f].z = o[2]; goff[f].w = o[3];
+    }
+    std::vector<unsigned short> perm_in(p->N2), perm_out(p->N2 + 1);
+    if (slicq_slice_perm(L, perm_in.data(), perm_out.data()) != 0) {
+        delete p;
+        return fail(SLICQ_E_UNSUPPORTED, "no slice-FFT permutation for this slice length");
     }
 
     SlicqDeviceTables& d = p->dev;
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
+    d.pad_l = pad_l; d.pad_r = pad_r; d.tw_lo = tw_lo; d.tw_hi = tw_hi;
     int rc = 0;
     rc |= upload(tuk, &d.tukey, p->owned);
     rc |= upload(wf, &d.wf, p->owned);
@@ -255,17 +323,26 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(p->bin_coff, &d.bin_coff, p->owned);
     rc |= upload(post, &d.post_tw, p->owned);
     rc |= upload(tw, &d.tw, p->owned);
-    rc |= upload(jlo, &d.jlo, p->owned);
-    rc |= upload(jcnt, &d.jcnt, p->owned);
+    rc |= upload(goff, &d.goff, p->owned);
+    rc |= upload(perm_in, &d.perm_in, p->owned);
+    rc |= upload(perm_out, &d.perm_out, p->owned);
     if (rc) {
         slicq_plan_destroy(p);
         return fail(SLICQ_E_CUDA, "device table upload failed");
     }
-    p->spec_stride_fwd = p->N2 + 2;  // N2+1 bins, padded to an even count (16-byte rows)
+    p->spec_stride_fwd = (pad_l + p->N2 + 1 + pad_r + 1) & ~1LL;  // even: 16-byte aligned rows
     const char* env = getenv("SLICQ_CHUNK_MB");
-    long long mb = env ? atoll(env) : 40;
+    long long mb = env ? atoll(env) : 1024;
     if (mb < 1) mb = 1;
     p->chunk_bytes = mb << 20;
+    const char* envj = getenv("SLICQ_BINS_JOBS");
+    p->target_jobs = envj ? atoi(envj) : 1184;   // 148 SMs x 2-4 resident CTAs x 2-4 waves
+    if (p->target_jobs < 1) p->target_jobs = 1;
+    const char* envb = getenv("SLICQ_ONLY_BUCKET");
+    p->only_bucket = envb ? atoi(envb) : -1;
+    const char* envi = getenv("SLICQ_BINS_MIN_ITERS");
+    p->min_iters = envi ? atoi(envi) : 4;
+    if (p->min_iters < 1) p->min_iters = 1;
     *out = p;
     return SLICQ_OK;
 }
@@ -294,6 +371,7 @@ long long bytes_per_unit(const slicq_plan* p, int inverse) {
 }
 long long chunk_units(const slicq_plan* p, int inverse) {
     long long c = p->chunk_bytes / bytes_per_unit(p, inverse);
+    if (c >= 296) c -= c % 296;   // whole waves of the slice kernels (148 SMs x 2 CTAs)
     return c < 1 ? 1 : c;
 }
 }  // namespace
@@ -308,19 +386,31 @@ extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64
 
 namespace {
 int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqBinsParams& bp, int n_rs) {
-    int tiles = 0;
+    int jobs = 0;
     bp.n_buckets = (int)p->buckets.size();
+    double total = 0.0;
+    for (const Bucket& b : p->buckets) total += b.cost;
     for (size_t i = 0; i < p->buckets.size(); ++i) {
         const Bucket& b = p->buckets[i];
         SlicqBucketArg& a = bp.b[i];
         a.ptr = reinterpret_cast<float2*>(views[i].ptr);
         a.s_row = views[i].s_row; a.s_bin = views[i].s_bin; a.s_slice = views[i].s_slice;
-        a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.G = b.G; a.tw_off = b.tw_off;
-        a.kind = b.kind; a.A = b.A; a.B = b.B; a.pad_ = 0;
-        a.tile_start = tiles;
-        tiles += (n_rs + b.G - 1) / b.G;
+        a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.gt = b.gt; a.tw_off = b.tw_off;
+        if (p->only_bucket >= 0 && (int)i != p->only_bucket) {       // tuning aid: time one bucket alone
+            a.units_per_job = b.gt; a.n_jobs = 0; a.job_start = jobs;
+            continue;
+        }
+        const int groups = (n_rs + b.gt - 1) / b.gt;                 // iterations available in this chunk
+        int nj = (int)(p->target_jobs * b.cost / total + 0.5);
+        if (nj > groups / p->min_iters) nj = groups / p->min_iters;
+        if (nj < 1) nj = 1;
+        const int gpj = (groups + nj - 1) / nj;                      // iterations per job
+        a.units_per_job = gpj * b.gt;
+        a.n_jobs = (n_rs + a.units_per_job - 1) / a.units_per_job;
+        a.job_start = jobs;
+        jobs += a.n_jobs;
     }
-    return tiles;
+    return jobs;
 }
 }  // namespace
 
@@ -351,8 +441,8 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
         ++g_launches;
         if (rc) break;
         bp->n_rs = n; bp->rs0 = (int)u0;
-        const int tiles = fill_bins_params(p, buckets, *bp, n);
-        { ProfScope ps(K_BINS_FWD, s); rc = slicq_launch_bins(bp, tiles, p->bins_smem, 0, s); }
+        const int jobs = fill_bins_params(p, buckets, *bp, n);
+        { ProfScope ps(K_BINS_FWD, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 0, s); }
         ++g_launches;
     }
     delete bp;
@@ -388,13 +478,13 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
     SlicqOlaParams op;
     memset(&op, 0, sizeof op);
     op.u = U; op.L = p->L; op.hop = p->hop; op.S = (int)n_slices; op.y = y; op.y_row_stride = y_row_stride;
-    op.length = length; op.k0 = k0; op.t0 = t0; op.halo_out = halo_out; op.scale = 1.f;
+    op.length = length; op.k0 = k0; op.t0 = t0; op.halo_out = halo_out; op.pieces = 4;
     int rc = 0;
     for (long long u0 = 0; u0 < units && rc == 0; u0 += cu) {
         const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
         bp->n_rs = n; bp->rs0 = (int)u0;
-        const int tiles = fill_bins_params(p, buckets, *bp, n);
-        { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, tiles, p->bins_smem, 1, s); }
+        const int jobs = fill_bins_params(p, buckets, *bp, n);
+        { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 1, s); }
         ++g_launches;
         if (rc) break;
         sp.n_rs = n; sp.rs0 = (int)u0;

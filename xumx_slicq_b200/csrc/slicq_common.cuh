@@ -2,12 +2,11 @@
 //
 // Build modes:
 //   nvcc (product):  real CUDA, sm_100a.
-//   g++ -DSLICQ_EMU (tests only): the *same kernel source* is compiled for the host and
-//       every CTA is executed by ONE emulated thread (blockDim = 1).  All kernels in
-//       this library are written as block-stride task loops separated by
-//       __syncthreads(), with no warp-level primitives, so a 1-thread CTA computes
-//       bit-for-bit the same task results.  The emulation library is test
-//       infrastructure (tests/emu): the product loader never loads it.
+//   g++ -DSLICQ_EMU (tests only): the *same kernel source* is compiled for the host; CTAs run
+//       one after the other, each with blockDim.x real OS threads and a barrier standing in
+//       for __syncthreads().  The kernels use no warp-level primitives, so this executes the
+//       same per-thread code paths as the GPU.  The emulation library is test infrastructure
+//       (tests/emu): the product loader never loads it.
 #pragma once
 
 #include <stdint.h>
@@ -20,17 +19,23 @@
 #include <cstring>
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
-extern dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local dim3 threadIdx;
+extern dim3 blockIdx, blockDim, gridDim;
 extern unsigned char* slicq_emu_smem;
+void slicq_emu_sync();                       // CTA barrier between the emulated threads
+#include <functional>
+void slicq_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __grid_constant__
-static inline void __syncthreads() {}
+static inline void __syncthreads() { slicq_emu_sync(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -47,17 +52,8 @@ static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 #define SLICQ_SET_SMEM(kern, bytes) (0)
 #define SLICQ_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(slicq_emu_smem)
-#define SLICQ_LAUNCH(kern, grid, block, smem, stream, ...)                         \
-    do {                                                                           \
-        dim3 g_ = (grid);                                                          \
-        gridDim = g_; blockDim = dim3(1, 1, 1); threadIdx = dim3(0, 0, 0);         \
-        for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                  \
-            for (unsigned by_ = 0; by_ < g_.y; ++by_)                              \
-                for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) {                        \
-                    blockIdx = dim3(bx_, by_, bz_);                                \
-                    kern(__VA_ARGS__);                                             \
-                }                                                                  \
-    } while (0)
+#define SLICQ_LAUNCH(kern, grid, block, smem, stream, ...) \
+    slicq_emu_launch((grid), (block), [&]() { kern(__VA_ARGS__); })
 #else
 // ------------------------------------------------------------------ real CUDA
 #include <cuda_runtime.h>
@@ -94,16 +90,21 @@ struct SlicqDeviceTables {
     int n_bins;     // J   (263)
     int n_buckets;  // 70
     int sum_M;      // 18640 coefficients per (row, slice)
+    int pad_l;      // spectrum rows carry pad_l mirrored bins below DC ...
+    int pad_r;      // ... and pad_r mirrored bins above Nyquist (bins never need reflection logic)
+    int tw_lo, tw_hi;       // support of the slicing window: tukey[p] != 0 only for p in [tw_lo, tw_hi)
     const float* tukey;     // [L]   slicing window
-    const float* wf;        // [sum_M] analysis windows  g_j[m] * (-1)^(pos_j/2) / M_j
-    const float* wi;        // [sum_M] synthesis windows gd_j[m] * M_j * (-1)^(pos_j/2)
+    // windows are stored in *centred* order m' = m~ + M/2 (m~ in [-M/2, M/2) the offset from pos_j)
+    const float* wf;        // [sum_M] analysis windows  g_j * (-1)^(pos_j/2) / M_j
+    const float* wi;        // [sum_M] synthesis windows gd_j * M_j * (-1)^(pos_j/2)
     const int* bin_pos;     // [J]  centre position (rfbas_j)
     const int* bin_M;       // [J]
     const int* bin_coff;    // [J]  offset of bin j inside a packed [sum_M] row
     const float2* post_tw;  // [N2/2 + 1]  exp(-2 pi i k / L)
     const float2* tw;       // concatenated per-bucket twiddles exp(-2 pi i j / M_b), j in [0, M_b)
-    const unsigned short* jlo;  // [N2 + 1] first bin covering spectrum position f
-    const unsigned char* jcnt;  // [N2 + 1] number of consecutive bins covering f (<= 8)
+    const int4* goff;       // [N2 + 1] offsets (into a packed synthesis row) of the <= 4 bins covering f, -1 = none
+    const unsigned short* perm_in;   // [N2]     shared-memory slot of FFT input index n
+    const unsigned short* perm_out;  // [N2 + 1] shared-memory slot of FFT output index k (entry N2 == entry 0)
 };
 
 // one bucket as a kernel sees it for one call (pointer + strides of the caller's tensor)
@@ -115,16 +116,16 @@ struct SlicqBucketArg {
     int M;
     int first_bin;
     int n_bins;
-    int G;                // (row,slice) units per tile
+    int gt;               // (row,slice) units processed concurrently by one CTA iteration
     int tw_off;           // offset into SlicqDeviceTables::tw
-    int tile_start;       // first tile index of this bucket inside the launch
-    int kind, A, B;       // FFT plan of this size (see fft_sizes.inc)
-    int pad_;
+    int job_start;        // first job (CTA) index of this bucket inside the launch
+    int n_jobs;           // CTAs working on this bucket
+    int units_per_job;    // multiple of gt
 };
 
 struct SlicqBinsParams {
     SlicqDeviceTables t;
-    float2* spec;          // forward: half spectra H [n_rs][spec_stride] ; inverse: packed T [n_rs][spec_stride]
+    float2* spec;          // analysis: padded half spectra H [n_rs][spec_stride] ; synthesis: packed T [n_rs][spec_stride]
     long long spec_stride;
     int n_rs;              // (row,slice) units in this chunk
     int rs0;               // flattened index (row * S + slice) of the first unit of the chunk
@@ -157,5 +158,5 @@ struct SlicqOlaParams {
     long long k0;          // global slice index of local slice 0
     long long t0;          // global sample index of y[.,0]
     float* halo_out;       // [rows][hop] or null: receives the first half of local slice 0 when k0 > 0
-    float scale;
+    int pieces;            // each hop is split into `pieces` CTAs
 };

@@ -1,187 +1,369 @@
-// Batched small-FFT engine shared by the analysis (per-bin IFFT) and synthesis (per-bin FFT)
-// kernels.  One CTA processes a tile of `nf` independent length-M transforms (all bins of one
-// bucket x G (row,slice) units).  Three compile-time plans per M (fft_sizes.inc):
-//   kind 1  one thread owns a whole DFT-M in registers,
-//   kind 2  two passes A x B through shared memory (Cooley-Tukey, table twiddles),
-//   kind 3  M = P * R with a prime P >= 29: the DFT-P runs as two real symmetric
-//           half-transforms (rdft_sym<P>, real and imaginary part on separate threads)
-//           followed by a combine step; the DFT-R is a register codelet.
-// Loaders / storers are functors with   Ctx begin(int i)   and  get<M>(ctx, m) / put(ctx, k, v).
-// Every loop is a block-stride task loop so the code is blockDim agnostic (see slicq_common.cuh).
+// Batched small-FFT engine of the analysis (per-bin IFFT) and synthesis (per-bin FFT) kernels.
+//
+// A CTA ("job") owns ONE bucket (F bins of equal length M) and a contiguous range of (row,slice)
+// units, and walks the range `gt` units at a time.  Everything that does not depend on the unit
+// -- the thread's bin, its position inside the transform, its window coefficients -- is computed
+// once per job and kept in registers; the per-unit work is loads, one register codelet, a
+// shared-memory transpose, the second codelet and stores.  Because a CTA executes a single M for
+// its whole life, only that size's straight-line codelets are live in the instruction cache.
+//
+// Index conventions.  Windows and spectrum reads use the *centred* order m' = m~ + M/2 with
+// m~ in [-M/2, M/2) the offset from the bin centre: x'[m'] = H[pos - M/2 + m'] (contiguous, no
+// wrap, no reflection thanks to the mirrored margins of H).  The reference's ifftshift is the
+// circular shift by M/2, which in the transform domain is the sign (-1)^n:
+//     analysis   c[n]  = (-1)^n * IDFT_M(x' * wf')[n]
+//     synthesis  T'[m'] = wi'[m'] * DFT_M((-1)^n c[n])[m']
+// Plans per M (fft_sizes.inc): kind 1 = one thread per transform, kind 2 = A x B Cooley-Tukey
+// through shared memory, kind 3 = prime P >= 29 times R via the real symmetric half transforms.
 #pragma once
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
 
-// ---------------------------------------------------------------------------------------
+struct JobCtx {
+    int u0, u1;     // unit range of this job (indices local to the chunk)
+    int F;          // bins in the bucket
+    int gt;         // units per iteration
+    int first_bin;
+    int rs0, S;     // chunk origin and slices per row: unit g is (row, k) = divmod(rs0 + g, S)
+};
+
+SLICQ_DEVFN float2 cneg_if(float2 v, bool neg) { return neg ? make_float2(-v.x, -v.y) : v; }
+
+// The first SLOT_BYTES of a job's shared memory hold, for the units of the current iteration, the
+// element offset of (row, bin f, slice k, 0) in the caller's bucket tensor: slot = gs * F + f.
+// One integer division per slot and iteration instead of one per coefficient.
+#define SLICQ_SLOT_BYTES 2048
+SLICQ_DEVFN void fill_slot_off(long long* so, const SlicqBucketArg& b, const JobCtx& j, int base, int ng) {
+    for (int t = threadIdx.x; t < ng * j.F; t += blockDim.x) {
+        const int gs = t / j.F, f = t - gs * j.F;
+        const int rs = j.rs0 + base + gs;
+        const int row = rs / j.S, k = rs - row * j.S;
+        so[t] = row * b.s_row + f * b.s_bin + k * b.s_slice;
+    }
+}
+
+// =========================================================================================
 // kind 1
-template <int M, bool INV, class Load, class Store>
-SLICQ_DEVFN void fft_tile_single(int nf, const Load& ld, const Store& st) {
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-        float2 v[M];
-        typename Load::Ctx lc = ld.begin(i);
+// =========================================================================================
+template <int M>
+SLICQ_DEVFN void ana_single(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
+    constexpr int PITCH = M + 1;
+    const int tid = threadIdx.x;
+    const int gs = tid / j.F, f = tid - gs * j.F;
+    const bool act = gs < j.gt;
+    float w[M];
+    int hoff = 0;
+    if (act) {
+        const int bin = j.first_bin + f;
+        const int coff = __ldg(p.t.bin_coff + bin);
+        hoff = p.t.pad_l + __ldg(p.t.bin_pos + bin) - M / 2;
 #pragma unroll
-        for (int m = 0; m < M; ++m) v[m] = ld.template get<M>(lc, m);
-        dft<M, INV>(v);
-        typename Store::Ctx sc = st.begin(i);
-#pragma unroll
-        for (int k = 0; k < M; ++k) st.put(sc, k, v[k]);
+        for (int m = 0; m < M; ++m) w[m] = __ldg(p.t.wf + coff + m);
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// kind 2 : x[B*n1 + n2] -> X[k1 + A*k2]
-template <int A, int B>
-struct TwoPassLayout {
-    static constexpr int BP = (B % 2 == 0) ? B + 1 : B;  // odd row pitch: conflict-free column reads
-    static constexpr int PER_FFT = A * BP;               // float2 elements of scratch per transform
-};
-
-template <int M, int A, int B, bool INV, class Load, class Store>
-SLICQ_DEVFN void fft_tile_two_pass(int nf, float2* sm, const float2* __restrict__ tw, const Load& ld,
-                                   const Store& st) {
-    static_assert(A * B == M, "bad split");
-    typedef TwoPassLayout<A, B> Lay;
-    // pass 1: DFT-A over n1 for every (transform, n2), twiddle, park in shared memory
-    for (int t = threadIdx.x; t < nf * B; t += blockDim.x) {
-        const int i = t / B, n2 = t - i * B;
-        float2 v[A];
-        typename Load::Ctx lc = ld.begin(i);
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float2);
+    float2* stage = sm + (gs * j.F + f) * PITCH;
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int g = base + gs;
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        if (act && g < j.u1) {
+            const float4* h = reinterpret_cast<const float4*>(p.spec + (long long)g * p.spec_stride + hoff);
+            float2 v[M];
 #pragma unroll
-        for (int n1 = 0; n1 < A; ++n1) v[n1] = ld.template get<M>(lc, B * n1 + n2);
-        dft<A, INV>(v);
-        float2* dst = sm + i * Lay::PER_FFT + n2;
-        dst[0] = v[0];
+            for (int m = 0; m < M; m += 2) {
+                const float4 x = h[m >> 1];
+                v[m] = make_float2(x.x * w[m], x.y * w[m]);
+                v[m + 1] = make_float2(x.z * w[m + 1], x.w * w[m + 1]);
+            }
+            dft<M, true>(v);
 #pragma unroll
-        for (int k1 = 1; k1 < A; ++k1) {
-            const float2 w = __ldg(tw + n2 * k1);
-            dst[k1 * Lay::BP] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
+            for (int n = 0; n < M; ++n) stage[n] = cneg_if(v[n], n & 1);
         }
-    }
-    __syncthreads();
-    // pass 2: DFT-B over n2 for every (transform, k1)
-    for (int t = threadIdx.x; t < nf * A; t += blockDim.x) {
-        const int i = t / A, k1 = t - i * A;
-        float2 v[B];
-        const float2* src = sm + i * Lay::PER_FFT + k1 * Lay::BP;
-#pragma unroll
-        for (int n2 = 0; n2 < B; ++n2) v[n2] = src[n2];
-        dft<B, INV>(v);
-        typename Store::Ctx sc = st.begin(i);
-#pragma unroll
-        for (int k2 = 0; k2 < B; ++k2) st.put(sc, k1 + A * k2, v[k2]);
+        __syncthreads();
+        for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
+            const int slot = t / M, n = t - slot * M;
+            b.ptr[so[slot] + n] = sm[slot * PITCH + n];
+        }
+        __syncthreads();
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// kind 3, prime first (analysis side):  x[R*n1 + n2], n1 in [0,P)  ->  X[k1 + P*k2]
-//   pass 1: rdft_sym<P> on (transform, n2, re|im)         tasks nf*R*2
-//   pass 2: combine + twiddle + DFT-R on (transform, k1)   tasks nf*P   (output runs of P)
-template <int P, int R>
-struct PrimeLayout {
-    static constexpr int PER_FFT = R * 2 * P;  // floats of scratch per transform
-};
+template <int M>
+SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
+    constexpr int PITCH = M + 1;
+    const int tid = threadIdx.x;
+    const int gs = tid / j.F, f = tid - gs * j.F;
+    const bool act = gs < j.gt;
+    float w[M];
+    int coff = 0;
+    if (act) {
+        coff = __ldg(p.t.bin_coff + j.first_bin + f);
+#pragma unroll
+        for (int m = 0; m < M; ++m) w[m] = __ldg(p.t.wi + coff + m);
+    }
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float2);
+    const float2* stage = sm + (gs * j.F + f) * PITCH;
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        __syncthreads();
+        for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
+            const int slot = t / M, n = t - slot * M;
+            sm[slot * PITCH + n] = b.ptr[so[slot] + n];
+        }
+        __syncthreads();
+        const int g = base + gs;
+        if (act && g < j.u1) {
+            float2 v[M];
+#pragma unroll
+            for (int n = 0; n < M; ++n) v[n] = cneg_if(stage[n], n & 1);
+            dft<M, false>(v);
+            float4* o = reinterpret_cast<float4*>(p.spec + (long long)g * p.spec_stride + coff);
+#pragma unroll
+            for (int m = 0; m < M; m += 2)
+                o[m >> 1] = make_float4(v[m].x * w[m], v[m].y * w[m], v[m + 1].x * w[m + 1], v[m + 1].y * w[m + 1]);
+        }
+        __syncthreads();
+    }
+}
 
-template <int M, int P, int R, bool INV, class Load, class Store>
-SLICQ_DEVFN void fft_tile_prime_first(int nf, float* sm, const float2* __restrict__ tw, const Load& ld,
-                                      const Store& st) {
+// =========================================================================================
+// kind 2 : M = A * B, A >= B
+// =========================================================================================
+// analysis: x'[B*n1 + n2] -> X[k1 + A*k2];  pass 1 = DFT-A (hoisted window), pass 2 = DFT-B (runs of A to HBM)
+template <int M, int A, int B>
+SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
+    static_assert(A * B == M, "bad split");
+    constexpr int BP = (B % 2 == 0) ? B + 1 : B;
+    constexpr int PER = A * BP;
+    const int tid = threadIdx.x;
+    const int per1 = j.F * B;
+    const int gs1 = tid / per1, r1 = tid - gs1 * per1;
+    const int f1 = r1 / B, n2 = r1 - f1 * B;
+    const bool act1 = gs1 < j.gt;
+    float w[A];
+    int hoff = 0;
+    if (act1) {
+        const int bin = j.first_bin + f1;
+        const int coff = __ldg(p.t.bin_coff + bin);
+        hoff = p.t.pad_l + __ldg(p.t.bin_pos + bin) - M / 2 + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < A; ++n1) w[n1] = __ldg(p.t.wf + coff + B * n1 + n2);
+    }
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float2);
+    float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
+    const float2* __restrict__ tw = p.t.tw + b.tw_off + 0;
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int g = base + gs1;
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        if (act1 && g < j.u1) {
+            const float2* h = p.spec + (long long)g * p.spec_stride + hoff;
+            float2 v[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; ++n1) {
+                const float2 x = h[B * n1];
+                v[n1] = make_float2(x.x * w[n1], x.y * w[n1]);
+            }
+            dft<A, true>(v);
+            y1[0] = v[0];
+#pragma unroll
+            for (int k1 = 1; k1 < A; ++k1)
+                y1[k1 * BP] = cneg_if(cmul_conj(v[k1], __ldg(tw + n2 * k1)), k1 & 1);  // (-1)^k1 folded here
+        }
+        __syncthreads();
+        for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
+            const int slot = t / A, k1 = t - slot * A;
+            const float2* src = sm + slot * PER + k1 * BP;
+            float2 v[B];
+#pragma unroll
+            for (int n = 0; n < B; ++n) v[n] = src[n];
+            dft<B, true>(v);
+            float2* o = b.ptr + so[slot] + k1;
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) o[A * k2] = cneg_if(v[k2], (A * k2) & 1);
+        }
+        __syncthreads();
+    }
+}
+
+// synthesis: x[A*n1 + n2] -> X[k1 + B*k2];  pass 1 = DFT-B (runs of A from HBM), pass 2 = DFT-A (hoisted window)
+template <int M, int A, int B>
+SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
+    static_assert(A * B == M, "bad split");
+    constexpr int AP = (A % 2 == 0) ? A + 1 : A;
+    constexpr int PER = B * AP;
+    const int tid = threadIdx.x;
+    const int per2 = j.F * B;
+    const int gs2 = tid / per2, r2 = tid - gs2 * per2;
+    const int f2 = r2 / B, k1h = r2 - f2 * B;
+    const bool act2 = gs2 < j.gt;
+    float w[A];
+    int coff = 0;
+    if (act2) {
+        coff = __ldg(p.t.bin_coff + j.first_bin + f2) + k1h;
+#pragma unroll
+        for (int k2 = 0; k2 < A; ++k2) w[k2] = __ldg(p.t.wi + coff + B * k2);
+    }
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float2);
+    const float2* y2 = sm + (gs2 * j.F + f2) * PER + k1h * AP;
+    const float2* __restrict__ tw = p.t.tw + b.tw_off;
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        __syncthreads();
+        for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
+            const int slot = t / A, n2 = t - slot * A;
+            const float2* src = b.ptr + so[slot] + n2;
+            const bool odd = n2 & 1;
+            float2 v[B];
+#pragma unroll
+            for (int n1 = 0; n1 < B; ++n1) v[n1] = cneg_if(src[A * n1], odd != (((A * n1) & 1) != 0));
+            dft<B, false>(v);
+            float2* dst = sm + slot * PER + n2;
+            dst[0] = v[0];
+#pragma unroll
+            for (int k1 = 1; k1 < B; ++k1) dst[k1 * AP] = cmul(v[k1], __ldg(tw + n2 * k1));
+        }
+        __syncthreads();
+        const int g = base + gs2;
+        if (act2 && g < j.u1) {
+            float2 v[A];
+#pragma unroll
+            for (int n = 0; n < A; ++n) v[n] = y2[n];
+            dft<A, false>(v);
+            float2* o = p.spec + (long long)g * p.spec_stride + coff;
+#pragma unroll
+            for (int k2 = 0; k2 < A; ++k2) o[B * k2] = make_float2(v[k2].x * w[k2], v[k2].y * w[k2]);
+        }
+        __syncthreads();
+    }
+}
+
+// =========================================================================================
+// kind 3 : M = P * R, P prime >= 29, R in {4, 8}
+// =========================================================================================
+// analysis (prime first): x'[R*n1 + n2], n1 in [0,P) -> X[k1 + P*k2]
+template <int M, int P, int R>
+SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* sm) {
     static_assert(P * R == M, "bad split");
     constexpr int H = (P - 1) / 2;
-    for (int t = threadIdx.x; t < nf * R * 2; t += blockDim.x) {
-        const int c = t & 1;
-        const int u = t >> 1;
-        const int i = u / R, n2 = u - i * R;
-        float x[P];
-        typename Load::Ctx lc = ld.begin(i);
+    const int tid = threadIdx.x;
+    const float2* __restrict__ tw = p.t.tw + b.tw_off;
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float);
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        // pass 1: real symmetric half transforms, task = (unit, bin, n2, re|im)
+        for (int t = tid; t < ng * j.F * R * 2; t += blockDim.x) {
+            const int c = t & 1, u = t >> 1;
+            const int slot = u / R, n2 = u - slot * R;
+            const int gs = slot / j.F, f = slot - gs * j.F;
+            const int bin = j.first_bin + f;
+            const float* wv = p.t.wf + __ldg(p.t.bin_coff + bin) + n2;
+            const float* h = reinterpret_cast<const float*>(
+                                 p.spec + (long long)(base + gs) * p.spec_stride + p.t.pad_l + __ldg(p.t.bin_pos + bin) - M / 2 + n2) + c;
+            float x[P];
 #pragma unroll
-        for (int n1 = 0; n1 < P; ++n1) {
-            const float2 v = ld.template get<M>(lc, R * n1 + n2);
-            x[n1] = c ? v.y : v.x;
+            for (int n1 = 0; n1 < P; ++n1) x[n1] = h[2 * R * n1] * __ldg(wv + R * n1);
+            rdft_sym<P>(x, sm + (size_t)(u * 2 + c) * P, 1);
         }
-        rdft_sym<P>(x, sm + (size_t)(u * 2 + c) * P, 1);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nf * P; t += blockDim.x) {
-        const int i = t / P, k1 = t - i * P;
-        const int kk = k1 <= H ? k1 : P - k1;
-        float2 v[R];
+        __syncthreads();
+        // pass 2: combine (inverse direction), twiddle, DFT-R, store runs of P
+        for (int t = tid; t < ng * j.F * P; t += blockDim.x) {
+            const int slot = t / P, k1 = t - slot * P;
+            const int kk = k1 <= H ? k1 : P - k1;
+            const bool minus = k1 > H;       // inverse: X[kk] = (Ar - Bi, Ai + Br), X[P-kk] = (Ar + Bi, Ai - Br)
+            const bool odd = k1 & 1;
+            float2 v[R];
 #pragma unroll
-        for (int n2 = 0; n2 < R; ++n2) {
-            const float* re = sm + (size_t)((i * R + n2) * 2) * P;
+            for (int n2 = 0; n2 < R; ++n2) {
+                const float* re = sm + (size_t)((slot * R + n2) * 2) * P;
+                const float* im = re + P;
+                float2 y = make_float2(re[kk], im[kk]);
+                if (k1 != 0) {
+                    float br = re[P - kk], bi = im[P - kk];
+                    if (minus) { br = -br; bi = -bi; }
+                    y.x -= bi;
+                    y.y += br;
+                }
+                if (n2 != 0 && k1 != 0) y = cmul_conj(y, __ldg(tw + n2 * k1));
+                v[n2] = cneg_if(y, odd);
+            }
+            dft<R, true>(v);
+            float2* o = b.ptr + so[slot] + k1;
+#pragma unroll
+            for (int k2 = 0; k2 < R; ++k2) o[P * k2] = cneg_if(v[k2], k2 & 1);   // P odd: (-1)^(P k2) = (-1)^k2
+        }
+        __syncthreads();
+    }
+}
+
+// synthesis (prime last): x[P*n1 + n2], n1 in [0,R) -> X[k1 + R*k2], k2 in [0,P)
+template <int M, int P, int R>
+SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* sm) {
+    static_assert(P * R == M, "bad split");
+    constexpr int H = (P - 1) / 2;
+    const int tid = threadIdx.x;
+    const float2* __restrict__ tw = p.t.tw + b.tw_off;
+    long long* so = reinterpret_cast<long long*>(sm);
+    sm += SLICQ_SLOT_BYTES / sizeof(float);
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        fill_slot_off(so, b, j, base, ng);
+        __syncthreads();
+        // pass 1: DFT-R + twiddle, task = (unit, bin, n2), input runs of P from HBM
+        for (int t = tid; t < ng * j.F * P; t += blockDim.x) {
+            const int slot = t / P, n2 = t - slot * P;
+            const float2* src = b.ptr + so[slot] + n2;
+            const bool odd = n2 & 1;
+            float2 v[R];
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) v[n1] = cneg_if(src[P * n1], odd != ((n1 & 1) != 0));  // (-1)^(P n1 + n2)
+            dft<R, false>(v);
+#pragma unroll
+            for (int k1 = 0; k1 < R; ++k1) {
+                float2 y = v[k1];
+                if (k1 != 0 && n2 != 0) y = cmul(y, __ldg(tw + n2 * k1));
+                float* re = sm + (size_t)((slot * R + k1) * 2) * P;
+                re[n2] = y.x;
+                re[P + n2] = y.y;
+            }
+        }
+        __syncthreads();
+        // pass 2a: real symmetric half transforms in place
+        for (int t = tid; t < ng * j.F * R * 2; t += blockDim.x) {
+            float* row = sm + (size_t)t * P;
+            float x[P];
+#pragma unroll
+            for (int n = 0; n < P; ++n) x[n] = row[n];
+            rdft_sym<P>(x, row, 1);
+        }
+        __syncthreads();
+        // pass 2b: combine (forward direction), dual window, store
+        for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
+            const int slot = t / M, r = t - slot * M;
+            const int k2 = r / R, k1 = r - k2 * R;
+            const int gs = slot / j.F, f = slot - gs * j.F;
+            const int kk = k2 <= H ? k2 : P - k2;
+            const float* re = sm + (size_t)((slot * R + k1) * 2) * P;
             const float* im = re + P;
             float2 y = make_float2(re[kk], im[kk]);
-            if (k1 != 0) {
+            if (k2 != 0) {
                 float br = re[P - kk], bi = im[P - kk];
-                // forward: X[kk] = (Ar + Bi, Ai - Br), X[P-kk] = (Ar - Bi, Ai + Br); inverse: swapped
-                const bool plus = (k1 <= H) != INV;
-                if (!plus) { br = -br; bi = -bi; }
+                if (k2 > H) { br = -br; bi = -bi; }   // forward: X[kk] = (Ar + Bi, Ai - Br), X[P-kk] = (Ar - Bi, Ai + Br)
                 y.x += bi;
                 y.y -= br;
             }
-            if (n2 != 0 && k1 != 0) {
-                const float2 w = __ldg(tw + n2 * k1);
-                y = INV ? cmul_conj(y, w) : cmul(y, w);
-            }
-            v[n2] = y;
+            const int coff = __ldg(p.t.bin_coff + j.first_bin + f) + r;
+            const float wv = __ldg(p.t.wi + coff);
+            p.spec[(long long)(base + gs) * p.spec_stride + coff] = make_float2(y.x * wv, y.y * wv);
         }
-        dft<R, INV>(v);
-        typename Store::Ctx sc = st.begin(i);
-#pragma unroll
-        for (int k2 = 0; k2 < R; ++k2) st.put(sc, k1 + P * k2, v[k2]);
-    }
-}
-
-// kind 3, prime last (synthesis side):  x[P*n1 + n2], n1 in [0,R)  ->  X[k1 + R*k2], k2 in [0,P)
-//   pass 1: DFT-R + twiddle on (transform, n2)             tasks nf*P   (input runs of P)
-//   pass 2: rdft_sym<P> in place on (transform, k1, re|im)  tasks nf*R*2
-//   pass 3: combine + store on (transform, k2, k1)          tasks nf*P*R
-template <int M, int P, int R, bool INV, class Load, class Store>
-SLICQ_DEVFN void fft_tile_prime_last(int nf, float* sm, const float2* __restrict__ tw, const Load& ld,
-                                     const Store& st) {
-    static_assert(P * R == M, "bad split");
-    constexpr int H = (P - 1) / 2;
-    for (int t = threadIdx.x; t < nf * P; t += blockDim.x) {
-        const int i = t / P, n2 = t - i * P;
-        float2 v[R];
-        typename Load::Ctx lc = ld.begin(i);
-#pragma unroll
-        for (int n1 = 0; n1 < R; ++n1) v[n1] = ld.template get<M>(lc, P * n1 + n2);
-        dft<R, INV>(v);
-#pragma unroll
-        for (int k1 = 0; k1 < R; ++k1) {
-            float2 y = v[k1];
-            if (k1 != 0 && n2 != 0) {
-                const float2 w = __ldg(tw + n2 * k1);
-                y = INV ? cmul_conj(y, w) : cmul(y, w);
-            }
-            float* re = sm + (size_t)((i * R + k1) * 2) * P;
-            re[n2] = y.x;
-            re[P + n2] = y.y;
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nf * R * 2; t += blockDim.x) {
-        float* row = sm + (size_t)t * P;
-        float x[P];
-#pragma unroll
-        for (int n = 0; n < P; ++n) x[n] = row[n];
-        rdft_sym<P>(x, row, 1);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nf * M; t += blockDim.x) {
-        const int i = t / M, r = t - i * M;
-        const int k2 = r / R, k1 = r - k2 * R;
-        const int kk = k2 <= H ? k2 : P - k2;
-        const float* re = sm + (size_t)((i * R + k1) * 2) * P;
-        const float* im = re + P;
-        float2 y = make_float2(re[kk], im[kk]);
-        if (k2 != 0) {
-            float br = re[P - kk], bi = im[P - kk];
-            const bool plus = (k2 <= H) != INV;
-            if (!plus) { br = -br; bi = -bi; }
-            y.x += bi;
-            y.y -= br;
-        }
-        typename Store::Ctx sc = st.begin(i);
-        st.put(sc, k1 + R * k2, y);
+        __syncthreads();
     }
 }
