@@ -263,7 +263,7 @@ def main():
     units_f, units_i = rows_f * S, rows_i * S
     kern = {}
     alg = {"slice_fft_fwd": B_IN * units_f, "bins_fwd": B_COEF * units_f, "bins_inv": B_COEF * units_i,
-           "slice_fft_inv": 0, "overlap_add": B_IN * units_i}
+           "slice_fft_inv": B_IN * units_i}
     tot_ms = 0.0
     for k, (ms, n) in prof.items():
         per_step = ms / nprof

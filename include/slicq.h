@@ -99,9 +99,9 @@ int64_t slicq_launch_count(void);
 
 /* Optional per-kernel timing with CUDA events on the launching stream (bench roofline accounting).
  * slicq_profile_read synchronises the recorded events, adds their durations (milliseconds) per
- * kernel id {0 slice_fft_fwd, 1 bins_fwd, 2 bins_inv, 3 slice_fft_inv, 4 overlap_add} and resets. */
+ * kernel id {0 slice_fft_fwd, 1 bins_fwd, 2 bins_inv, 3 slice_fft_inv (incl. overlap-add)} and resets. */
 int slicq_profile_enable(int on);
-int slicq_profile_read(double* ms /*[5]*/, int64_t* launches /*[5]*/);
+int slicq_profile_read(double* ms /*[4]*/, int64_t* launches /*[4]*/);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ EXPORTS = (
     "slicq_scratch_bytes", "slicq_forward", "slicq_inverse", "slicq_launch_count",
     "slicq_profile_enable", "slicq_profile_read",
 )
-KERNEL_NAMES = ("slice_fft_fwd", "bins_fwd", "bins_inv", "slice_fft_inv", "overlap_add")
+KERNEL_NAMES = ("slice_fft_fwd", "bins_fwd", "bins_inv", "slice_fft_inv")
 
 
 class SlicqTablesC(C.Structure):
@@ -87,8 +87,8 @@ def profile_enable(on: bool, lib: C.CDLL | None = None) -> None:
 
 def profile_read(lib: C.CDLL | None = None) -> dict:
     """{kernel name: (total ms, launches)} since the last read (synchronises the recorded events)."""
-    ms = (C.c_double * 5)()
-    n = (C.c_int64 * 5)()
+    ms = (C.c_double * 8)()
+    n = (C.c_int64 * 8)()
     (lib or load()).slicq_profile_read(ms, n)
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_NAMES)}
 

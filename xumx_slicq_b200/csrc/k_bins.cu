@@ -81,7 +81,7 @@ SLICQ_DEVFN void bins_body(const SlicqBinsParams& p, unsigned char* smem) {
 #define SLICQ_BINS_THREADS 256
 #endif
 #ifndef SLICQ_BINS_MIN_BLOCKS
-#define SLICQ_BINS_MIN_BLOCKS (512 / SLICQ_BINS_THREADS)
+#define SLICQ_BINS_MIN_BLOCKS (768 / SLICQ_BINS_THREADS)
 #endif
 
 __global__ void __launch_bounds__(SLICQ_BINS_THREADS, SLICQ_BINS_MIN_BLOCKS) bins_fwd_kernel(const __grid_constant__ SlicqBinsParams p) {

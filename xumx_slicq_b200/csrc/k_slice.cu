@@ -25,7 +25,7 @@
 #include "dft_codelets.cuh"
 
 #ifndef SLICQ_SLICE_THREADS
-#define SLICQ_SLICE_THREADS 256
+#define SLICQ_SLICE_THREADS 384
 #endif
 
 namespace {
@@ -214,12 +214,20 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 3b: one CTA per (row, slice).  packed windowed bin spectra T -> slice signal u [L]
+// stage 3b + 4: one CTA per (row, slice).  packed windowed bin spectra T -> slice signal u[L],
+// overlap-added straight into y:  y[(k-1)*hop + p] += u_k[p].  Every output sample is the sum of
+// exactly two slices, one even and one odd: the launch with parity 0 STORES the even slices, the
+// launch with parity 1 (stream-ordered after it) ACCUMULATES the odd ones -- no atomics, no
+// intermediate slice buffer, and a two-term sum is order independent (bitwise reproducible).
+// (reference: nsgt/unslicing.py:33-69, nsgt/slicq.py:207-230)
 template <class PF>
 __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
     constexpr int N = PF::N;
     const int rsl = blockIdx.x;
+    const int rs = p.rs0 + rsl;
+    const int row = rs / p.S, k = rs - row * p.S;
+    if ((k & 1) != p.parity) return;
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
     const unsigned short* __restrict__ pin = p.t.perm_in;
     constexpr int UG = 2;
@@ -260,61 +268,47 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     __syncthreads();
     pfa_passes<PF, true>(Z);
     const float scale = 1.0f / (float)(2 * N);
-    float2* __restrict__ U = reinterpret_cast<float2*>(p.u + (long long)rsl * (2 * N));
     const unsigned short* __restrict__ pout = p.t.perm_out;
+    // slice sample p = 2n, 2n+1 goes to y index tb + p;  first half (n < N/2) = hop k-1, second = hop k
+    const long long tb = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;
+    float* __restrict__ yr = p.x + row * p.x_row_stride;
+    const bool accumulate = p.parity != 0;
+    // the last slice of the call has no right neighbour: its second half is stored even when odd
+    const bool second_store = !accumulate || (k + 1 >= p.S);
+    const bool first_to_halo = (k == 0);      // hop -1: other shard (halo) or before the signal (dropped)
+    float* __restrict__ halo = (p.halo_out != nullptr && p.k0 > 0) ? p.halo_out + (long long)row * p.t.hop : nullptr;
+    const bool vec = ((reinterpret_cast<uintptr_t>(yr + tb) & 7) == 0) && tb >= 0 && tb + 2 * N <= p.T && !first_to_halo;
     constexpr int UO = 4;
     for (int n0 = threadIdx.x; n0 < N; n0 += UO * blockDim.x) {
         int po[UO];
-#pragma unroll
-        for (int u = 0; u < UO; ++u) if (n0 + u * blockDim.x < N) po[u] = __ldg(pout + n0 + u * blockDim.x);
+        float2 old[UO];
 #pragma unroll
         for (int u = 0; u < UO; ++u) {
             const int n = n0 + u * blockDim.x;
-            if (n < N) { const float2 z = Z[po[u]]; U[n] = make_float2(z.x * scale, z.y * scale); }
+            if (n < N) {
+                po[u] = __ldg(pout + n);
+                if (vec && (accumulate && (n < N / 2 || !second_store)))
+                    old[u] = *reinterpret_cast<const float2*>(yr + tb + 2 * n);
+            }
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// stage 4: overlap-add of the chunk's slices into y.
-//   out hop h (samples [h*hop, (h+1)*hop) of the padded signal) = second half of slice h
-//                                                                + first half of slice h+1.
-//   grid = (units, pieces, 2): z==0 -> "store" job of the unit's own hop, z==1 -> "carry" job
-//   (first half of a slice whose left neighbour was written by an earlier launch / other shard).
-__global__ void __launch_bounds__(256) overlap_add_kernel(const __grid_constant__ SlicqOlaParams p) {
-    const int rsl = blockIdx.x;
-    const int rs = p.rs0 + rsl;
-    const int row = rs / p.S, k = rs - row * p.S;
-    const float* __restrict__ u = p.u + (long long)rsl * p.L;
-    float* __restrict__ yr = p.y + row * p.y_row_stride;
-    const int q_lo = (int)(((long long)p.hop * blockIdx.y) / p.pieces);
-    const int q_hi = (int)(((long long)p.hop * (blockIdx.y + 1)) / p.pieces);
-    if (blockIdx.z == 0) {
-        const bool has_next = (k + 1 < p.S) && (rsl + 1 < p.n_rs);
-        const float* __restrict__ un = u + p.L;
-        const long long tb = (p.k0 + k) * (long long)p.hop - p.t0;
-        for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) {
-            const long long t = tb + q;
-            if (t < 0 || t >= p.length) continue;
-            float v = u[p.hop + q];
-            if (has_next) v += un[q];
-            yr[t] = v;
-        }
-    } else {
-        // first half of slice k belongs to hop k-1: only needed when slice k-1 is NOT in this chunk
-        const bool prev_in_chunk = (k > 0) && (rsl > 0);
-        if (prev_in_chunk) return;
-        if (k == 0) {
-            if (p.halo_out == nullptr || p.k0 == 0) return;  // hop -1 of the whole signal: dropped
-            float* __restrict__ h = p.halo_out + (long long)row * p.hop;
-            for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) h[q] = u[q];
-            return;
-        }
-        const long long tb = (p.k0 + k - 1) * (long long)p.hop - p.t0;
-        for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) {
-            const long long t = tb + q;
-            if (t < 0 || t >= p.length) continue;
-            yr[t] += u[q];
+#pragma unroll
+        for (int u = 0; u < UO; ++u) {
+            const int n = n0 + u * blockDim.x;
+            if (n >= N) continue;
+            const float2 z0 = Z[po[u]];
+            float2 z = make_float2(z0.x * scale, z0.y * scale);
+            const bool first = n < N / 2;
+            const bool add = accumulate && (first || !second_store);
+            if (vec) {
+                if (add) { z.x += old[u].x; z.y += old[u].y; }
+                *reinterpret_cast<float2*>(yr + tb + 2 * n) = z;
+            } else if (first && first_to_halo) {
+                if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
+            } else {
+                const long long t = tb + 2 * n;
+                if (t >= 0 && t < p.T) yr[t] = add ? yr[t] + z.x : z.x;
+                if (t + 1 >= 0 && t + 1 < p.T) yr[t + 1] = add ? yr[t + 1] + z.y : z.y;
+            }
         }
     }
 }
@@ -356,8 +350,3 @@ extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
-extern "C" int slicq_launch_ola(const SlicqOlaParams* p, cudaStream_t s) {
-    if (p->n_rs <= 0) return 0;
-    SLICQ_LAUNCH(overlap_add_kernel, dim3(p->n_rs, p->pieces, 2), dim3(256), 0, s, *p);
-    return (int)cudaGetLastError();
-}

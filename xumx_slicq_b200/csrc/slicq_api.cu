@@ -52,7 +52,6 @@ void slicq_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) 
 extern "C" int slicq_launch_bins(const SlicqBinsParams* p, int n_tiles, int smem_bytes, int synth, cudaStream_t s);
 extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s);
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s);
-extern "C" int slicq_launch_ola(const SlicqOlaParams* p, cudaStream_t s);
 extern "C" int slicq_slice_smem_bytes(int L);
 extern "C" int slicq_bins_threads(void);
 extern "C" int slicq_slice_perm(int L, unsigned short* perm_in, unsigned short* perm_out);
@@ -63,7 +62,7 @@ thread_local std::string g_err;
 long long g_launches = 0;
 
 // ---- optional per-kernel CUDA-event timing (bench.py roofline accounting) -----------------
-enum { K_SLICE_FWD = 0, K_BINS_FWD, K_BINS_INV, K_SLICE_INV, K_OLA, K_COUNT };
+enum { K_SLICE_FWD = 0, K_BINS_FWD, K_BINS_INV, K_SLICE_INV, K_COUNT };
 bool g_prof = false;
 #ifndef SLICQ_EMU
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -332,7 +331,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     }
     p->spec_stride_fwd = (pad_l + p->N2 + 1 + pad_r + 1) & ~1LL;  // even: 16-byte aligned rows
     const char* env = getenv("SLICQ_CHUNK_MB");
-    long long mb = env ? atoll(env) : 1024;
+    long long mb = env ? atoll(env) : 2048;
     if (mb < 1) mb = 1;
     p->chunk_bytes = mb << 20;
     const char* envj = getenv("SLICQ_BINS_JOBS");
@@ -341,7 +340,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     const char* envb = getenv("SLICQ_ONLY_BUCKET");
     p->only_bucket = envb ? atoi(envb) : -1;
     const char* envi = getenv("SLICQ_BINS_MIN_ITERS");
-    p->min_iters = envi ? atoi(envi) : 4;
+    p->min_iters = envi ? atoi(envi) : 1;
     if (p->min_iters < 1) p->min_iters = 1;
     *out = p;
     return SLICQ_OK;
@@ -367,7 +366,7 @@ extern "C" int64_t slicq_plan_num_slices(const slicq_plan* p, int64_t T) {
 namespace {
 long long bytes_per_unit(const slicq_plan* p, int inverse) {
     if (!inverse) return p->spec_stride_fwd * 8;
-    return (long long)p->sum_M * 8 + (long long)p->L * 4;
+    return (long long)p->sum_M * 8;
 }
 long long chunk_units(const slicq_plan* p, int inverse) {
     long long c = p->chunk_bytes / bytes_per_unit(p, inverse);
@@ -429,7 +428,7 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
     float2* H = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
     SlicqSliceParams sp;
     memset(&sp, 0, sizeof sp);
-    sp.t = p->dev; sp.x = x; sp.x_row_stride = x_row_stride; sp.T = n_samples; sp.t0 = t0; sp.k0 = k0;
+    sp.t = p->dev; sp.x = const_cast<float*>(x); sp.x_row_stride = x_row_stride; sp.T = n_samples; sp.t0 = t0; sp.k0 = k0;
     sp.spec = H; sp.spec_stride = p->spec_stride_fwd; sp.S = (int)n_slices;
     SlicqBinsParams* bp = new SlicqBinsParams();
     bp->t = p->dev; bp->spec = H; bp->spec_stride = p->spec_stride_fwd; bp->S = (int)n_slices;
@@ -469,31 +468,32 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
     const long long nu = units < cu ? units : cu;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
     float2* T = reinterpret_cast<float2*>(base);
-    float* U = reinterpret_cast<float*>(base + nu * (long long)p->sum_M * 8);
+    (void)nu;
     SlicqBinsParams* bp = new SlicqBinsParams();
     bp->t = p->dev; bp->spec = T; bp->spec_stride = p->sum_M; bp->S = (int)n_slices;
     SlicqSliceParams sp;
     memset(&sp, 0, sizeof sp);
-    sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->sum_M; sp.u = U; sp.S = (int)n_slices;
-    SlicqOlaParams op;
-    memset(&op, 0, sizeof op);
-    op.u = U; op.L = p->L; op.hop = p->hop; op.S = (int)n_slices; op.y = y; op.y_row_stride = y_row_stride;
-    op.length = length; op.k0 = k0; op.t0 = t0; op.halo_out = halo_out; op.pieces = 4;
+    sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->sum_M; sp.S = (int)n_slices;
+    sp.x = y; sp.x_row_stride = y_row_stride; sp.T = length; sp.t0 = t0; sp.halo_out = halo_out;
     int rc = 0;
-    for (long long u0 = 0; u0 < units && rc == 0; u0 += cu) {
-        const int n = (int)((units - u0 < cu) ? (units - u0) : cu);
-        bp->n_rs = n; bp->rs0 = (int)u0;
-        const int jobs = fill_bins_params(p, buckets, *bp, n);
+    for (long long u0 = 0; u0 < units && rc == 0;) {
+        long long n = (units - u0 < cu) ? (units - u0) : cu;
+        // a chunk must not start on an even slice k > 0: the odd slice before it accumulates into
+        // hops that the even slice has to have stored first (see slice_fft_inv_kernel)
+        while (n > 1 && u0 + n < units && ((u0 + n) % n_slices) != 0 && (((u0 + n) % n_slices) & 1) == 0) --n;
+        bp->n_rs = (int)n; bp->rs0 = (int)u0;
+        const int jobs = fill_bins_params(p, buckets, *bp, (int)n);
         { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 1, s); }
         ++g_launches;
         if (rc) break;
-        sp.n_rs = n; sp.rs0 = (int)u0;
-        { ProfScope ps(K_SLICE_INV, s); rc = slicq_launch_slice_inv(&sp, s); }
-        ++g_launches;
-        if (rc) break;
-        op.n_rs = n; op.rs0 = (int)u0;
-        { ProfScope ps(K_OLA, s); rc = slicq_launch_ola(&op, s); }
-        ++g_launches;
+        sp.n_rs = (int)n; sp.rs0 = (int)u0;
+        {
+            ProfScope ps(K_SLICE_INV, s);
+            sp.parity = 0; rc = slicq_launch_slice_inv(&sp, s);
+            if (!rc) { sp.parity = 1; rc = slicq_launch_slice_inv(&sp, s); }
+        }
+        g_launches += 2;
+        u0 += n;
     }
     delete bp;
     if (rc) {

@@ -20,6 +20,8 @@
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int a, int b) { int2 r; r.x = a; r.y = b; return r; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
@@ -136,27 +138,15 @@ struct SlicqBinsParams {
 
 struct SlicqSliceParams {
     SlicqDeviceTables t;
-    // forward: input signal ; inverse: unused
-    const float* x;
+    // forward: x = input signal rows ; inverse: y = output signal rows (same fields)
+    float* x;
     long long x_row_stride;
-    long long T;           // valid samples in x (per row)
-    long long t0;          // global sample index of x[.,0]
+    long long T;           // valid samples per row (forward: input length, inverse: output length)
+    long long t0;          // global sample index of x[.,0] / y[.,0]
     long long k0;          // global slice index of local slice 0
     float2* spec;          // forward: H out ; inverse: T in
     long long spec_stride;
-    float* u;              // inverse: slice time signals out [n_rs][L]
+    float* halo_out;       // inverse: [rows][hop] or null; first half of local slice 0 when k0 > 0
     int n_rs, rs0, S;
-};
-
-struct SlicqOlaParams {
-    const float* u;        // [n_rs][L]
-    int L, hop;
-    int n_rs, rs0, S;
-    float* y;              // [rows][y_row_stride]
-    long long y_row_stride;
-    long long length;      // valid output samples per row
-    long long k0;          // global slice index of local slice 0
-    long long t0;          // global sample index of y[.,0]
-    float* halo_out;       // [rows][hop] or null: receives the first half of local slice 0 when k0 > 0
-    int pieces;            // each hop is split into `pieces` CTAs
+    int parity;            // inverse: this launch handles slices with (k & 1) == parity
 };

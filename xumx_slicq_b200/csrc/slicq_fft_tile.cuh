@@ -190,55 +190,62 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     }
 }
 
-// synthesis: x[A*n1 + n2] -> X[k1 + B*k2];  pass 1 = DFT-B (runs of A from HBM), pass 2 = DFT-A (hoisted window)
+// synthesis: x[B*n1 + n2] -> X[k1 + A*k2];  same shape as the analysis: pass 1 = DFT-A with the
+// thread's (unit, bin, n2) fixed for the whole job (runs of B from the caller's tensor), pass 2 =
+// DFT-B, dual window, runs of A into the packed row T.
 template <int M, int A, int B>
 SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
     static_assert(A * B == M, "bad split");
-    constexpr int AP = (A % 2 == 0) ? A + 1 : A;
-    constexpr int PER = B * AP;
+    constexpr int BP = (B % 2 == 0) ? B + 1 : B;
+    constexpr int PER = A * BP;
     const int tid = threadIdx.x;
-    const int per2 = j.F * B;
-    const int gs2 = tid / per2, r2 = tid - gs2 * per2;
-    const int f2 = r2 / B, k1h = r2 - f2 * B;
-    const bool act2 = gs2 < j.gt;
-    float w[A];
-    int coff = 0;
-    if (act2) {
-        coff = __ldg(p.t.bin_coff + j.first_bin + f2) + k1h;
-#pragma unroll
-        for (int k2 = 0; k2 < A; ++k2) w[k2] = __ldg(p.t.wi + coff + B * k2);
-    }
-    long long* so = reinterpret_cast<long long*>(sm);
+    const int per1 = j.F * B;
+    const int gs1 = tid / per1, r1 = tid - gs1 * per1;
+    const int f1 = r1 / B, n2 = r1 - f1 * B;
+    const bool act1 = gs1 < j.gt;
+    const bool odd = n2 & 1;
+    // per-slot constants of pass 2 (do not change over the job): unit offset gs and row offset coff_f
+    int2* sc = reinterpret_cast<int2*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
-    const float2* y2 = sm + (gs2 * j.F + f2) * PER + k1h * AP;
+    for (int t = tid; t < j.gt * j.F; t += blockDim.x) {
+        const int gs = t / j.F, f = t - gs * j.F;
+        sc[t] = make_int2(gs, __ldg(p.t.bin_coff + j.first_bin + f));
+    }
+    float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
     const float2* __restrict__ tw = p.t.tw + b.tw_off;
+    const float* __restrict__ wi = p.t.wi;
+    __syncthreads();
     for (int base = j.u0; base < j.u1; base += j.gt) {
-        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
-        fill_slot_off(so, b, j, base, ng);
-        __syncthreads();
-        for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
-            const int slot = t / A, n2 = t - slot * A;
-            const float2* src = b.ptr + so[slot] + n2;
-            const bool odd = n2 & 1;
-            float2 v[B];
-#pragma unroll
-            for (int n1 = 0; n1 < B; ++n1) v[n1] = cneg_if(src[A * n1], odd != (((A * n1) & 1) != 0));
-            dft<B, false>(v);
-            float2* dst = sm + slot * PER + n2;
-            dst[0] = v[0];
-#pragma unroll
-            for (int k1 = 1; k1 < B; ++k1) dst[k1 * AP] = cmul(v[k1], __ldg(tw + n2 * k1));
-        }
-        __syncthreads();
-        const int g = base + gs2;
-        if (act2 && g < j.u1) {
+        const int g = base + gs1;
+        if (act1 && g < j.u1) {
+            const int rs = j.rs0 + g;
+            const int row = rs / j.S, k = rs - row * j.S;
+            const float2* src = b.ptr + row * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
             float2 v[A];
 #pragma unroll
-            for (int n = 0; n < A; ++n) v[n] = y2[n];
+            for (int n1 = 0; n1 < A; ++n1) v[n1] = cneg_if(src[B * n1], odd != (((B * n1) & 1) != 0));  // (-1)^(B n1 + n2)
             dft<A, false>(v);
-            float2* o = p.spec + (long long)g * p.spec_stride + coff;
+            y1[0] = v[0];
 #pragma unroll
-            for (int k2 = 0; k2 < A; ++k2) o[B * k2] = make_float2(v[k2].x * w[k2], v[k2].y * w[k2]);
+            for (int k1 = 1; k1 < A; ++k1) y1[k1 * BP] = cmul(v[k1], __ldg(tw + n2 * k1));
+        }
+        __syncthreads();
+        const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
+        for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
+            const int slot = t / A, k1 = t - slot * A;
+            const int2 c = sc[slot];
+            const float2* src = sm + slot * PER + k1 * BP;
+            float2 v[B];
+#pragma unroll
+            for (int n = 0; n < B; ++n) v[n] = src[n];
+            dft<B, false>(v);
+            const int off = c.y + k1;
+            float2* o = p.spec + (long long)(base + c.x) * p.spec_stride + off;
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) {
+                const float w = __ldg(wi + off + A * k2);
+                o[A * k2] = make_float2(v[k2].x * w, v[k2].y * w);
+            }
         }
         __syncthreads();
     }
