@@ -131,13 +131,71 @@ def cpu_reference_arm(steps: int, warmup: int, sample_seconds: float):
     return sample_seconds / dt, dt, cores, f"{sample_seconds:g} s stereo mixture: 1 forward (2 rows) + inverse of 4 targets (8 rows)"
 
 
+def bench_slices(args, nsg, dev, rank, world, distributed):
+    """BASELINE.json configs[3]: ONE synthetic 3-min stereo track; slices split into contiguous ranges
+    over the ranks, one half-slice halo message per boundary over NCCL (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from xumx_slicq_b200.sharding import SliceShardedSliCQT
+    Ttrack = 180 * FS
+    if distributed:
+        sh = SliceShardedSliCQT(nsg, Ttrack)
+        lo, hi = sh.lo, sh.hi
+    else:
+        sh, lo, hi = None, 0, Ttrack
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x_local = (torch.rand(2, Ttrack, device=dev, generator=gen) * 2 - 1)[:, lo:hi].contiguous()
+    gains = GAINS
+
+    def step():
+        C = sh.forward(x_local) if sh else nsg.forward_rows(x_local)
+        Yl = [torch.cat([c * g for g in gains], dim=0) for c in C]      # 4 targets x 2 channels (model stand-in)
+        return sh.inverse(Yl) if sh else nsg.backward_rows(Yl, Ttrack)
+
+    for _ in range(args.warmup):
+        y = step()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    stream = torch.cuda.current_stream(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        y = step()
+    b.record(stream)
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    err = float((y[:2] - gains[0] * x_local).abs().max())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "sliCQT fwd+inv audio-sec/sec", "value": 180.0 / (ms * 1e-3), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[3]: one synthetic 3-min stereo track (881 slices), 1 forward + 4-target "
+                                   "inverse, slices sharded in contiguous ranges, one [rows, 9030] fp32 halo message "
+                                   "per boundary and direction over NCCL; includes the torch stand-in for the model",
+                       "parallelism": f"slices x{world}"},
+            "max_abs_err_target0": err,
+        }))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="30 s mixtures per GPU per step")
+    ap.add_argument("--batch", type=int, default=8, help="30 s mixtures per GPU per step (Separator.forward takes a batch)")
+    ap.add_argument("--mode", default="tracks", choices=["tracks", "slices"],
+                    help="tracks: every rank demixes its own batch of 30 s mixtures (weak scaling, configs[1]); "
+                         "slices: ONE 3-min stereo track sharded by slice range with NCCL halo exchange (strong, configs[3])")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -147,9 +205,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    base_cfg = {"workload": "configs[1]: sliCQT path of a realtime demix of one synthetic 30 s 44.1 kHz stereo "
-                            "mixture (1 forward of 2 rows x 148 slices + inverse of 4 targets = 8 rows x 148 slices), "
-                            "Bark(262, 32.9 Hz), sllen 18060",
+    base_cfg = {"workload": "configs[1]: sliCQT path of a realtime demix of synthetic 30 s 44.1 kHz stereo mixtures "
+                            "(per mixture: 1 forward of 2 rows x 148 slices + inverse of 4 targets = 8 rows x 148 slices), "
+                            "Bark(262, 32.9 Hz), sllen 18060; one step = one batch of mixtures per GPU, as "
+                            "Separator.forward(audio[B,2,T]) processes them",
                 "mixtures_per_gpu_per_step": args.batch, "parallelism": f"tracks x{max(world, args.gpus)}",
                 "l2": "inputs+outputs of one step (>= 330 MB) exceed the 126 MB L2 and an extra 256 MB buffer is "
                       "written between timed steps"}
@@ -189,6 +248,8 @@ def main():
         base = NSGTBase(SCALE["scale"], SCALE["fbins"], SCALE["fmin"], device=dev)
     nsg = base.nsgt
     nsgt, insgt = make_filterbanks(base)
+    if args.mode == "slices":
+        return bench_slices(args, nsg, dev, rank, world, distributed)
     B = args.batch
     S = nsg.n_slices(T)
     rows_f, rows_i = 2 * B, 2 * B * N_TARGETS
@@ -322,6 +383,33 @@ def main():
     # ---- quality guard: the timed path really reconstructs (gain g of target t times the mixture)
     err = float((yout[:rows_f] - GAINS[0] * x).abs().max())
 
+    # ---- the same path for ONE mixture per step (latency view of configs[1]; launch-bound)
+    single = None
+    if world == 1 and B != 1:
+        x1 = x[:2]
+        Y1 = [torch.cat([c[2 * B * t: 2 * B * t + 2] for t in range(N_TARGETS)], 0).contiguous() for c in Y]
+        slab1, C1 = nsg.alloc_coefficients(2, S, dev)
+        vf1, vi1 = [nsg._view_of(c) for c in C1], [nsg._view_of(c) for c in Y1]
+        s1f, s1i = plan.scratch_bytes(2, S, False), plan.scratch_bytes(2 * N_TARGETS, S, True)
+        y1 = torch.empty(2 * N_TARGETS, T, device=dev)
+
+        def step1():
+            plan.forward(x1.data_ptr(), 2, x1.stride(0), T, 0, 0, S, vf1, scratch.data_ptr(), s1f, stream.cuda_stream)
+            plan.inverse(vi1, 2 * N_TARGETS, S, 0, y1.data_ptr(), y1.stride(0), T, 0, 0, scratch.data_ptr(), s1i,
+                         stream.cuda_stream)
+        for _ in range(3):
+            step1()
+        torch.cuda.synchronize(dev)
+        n1 = 20
+        ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n1)]
+        for a, b in ev1:
+            flush.fill_(1)
+            a.record(stream); step1(); b.record(stream)
+        torch.cuda.synchronize(dev)
+        ms1 = float(np.mean([a.elapsed_time(b) for a, b in ev1]))
+        single = {"mixtures_per_step": 1, "ms_per_step": ms1, "value": SECONDS / (ms1 * 1e-3), "unit": "audio-s/s",
+                  "roofline_frac": round(B_UNIT * (2 + 2 * N_TARGETS) * S / (ms1 * 1e-3) / 1e9 / peak, 4)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores, sample = cpu_reference_arm(3, 1, args.cpu_sample_seconds)
@@ -333,7 +421,8 @@ def main():
             "metric": "sliCQT fwd+inv audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_mixture": single,
+            "gpu_launches": int(launches),
             "clocks": clocks, "max_abs_err_target0": err,
         }))
     if distributed:

@@ -7,7 +7,7 @@ mkdir -p $OUT
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches_${TAG}.csv python tools/prof_step.py --batch 1 --steps 2 > $OUT/ncu_l.log 2>&1
 echo "launch list rc=$?"
-ncu --profile-from-start off --set full --cache-control none --clock-control none --import-source on -k regex:'slice_fft|overlap' -c 3 \
+ncu --profile-from-start off --set full --cache-control none --clock-control none --import-source on -k regex:'slice_fft' -c 3 \
     -o $OUT/prof_${TAG}_slice python tools/prof_step.py --batch 2 --steps 1 > $OUT/ncu_f1.log 2>&1
 echo "slice capture rc=$?"
 ncu --profile-from-start off --set full --cache-control none --clock-control none -k regex:'bins_' -c 2 \

@@ -1,0 +1,119 @@
+"""Multi-GPU sharding of the sliCQT path (one process per GPU, torch.distributed; NCCL on B200).
+
+The reference has no distributed code at all; this is new design for the
+two ways the path shards:
+
+* by track / batch row -- rows are independent in every stage: ``shard_tracks`` deals tracks to
+  ranks, there is no data-path communication.
+* by contiguous slice range of ONE long track -- every stage is per-slice independent except the
+  50 % overlap-add, which couples only adjacent slices.  Rank r owns slices [k0, k1) and the
+  samples of hops [k0, k1) (hop h = samples [h*hop, (h+1)*hop)).  Exactly ONE message per shard
+  boundary moves in each direction of the transform:
+    analysis : the left neighbour's last hop of *input* samples (slice k0 starts at (k0-1)*hop)
+    synthesis: the first half of slice k0 (``halo_out`` of the kernel), which belongs to the left
+               neighbour's last hop and is added there.
+  Every output sample is the sum of exactly two slices, so the sharded result is bitwise equal to
+  the unsharded one.
+
+Messages are ``[rows, hop]`` float32 (72 KB for a stereo track): latency-, not bandwidth-bound;
+they go through ``torch.distributed`` point-to-point ops (NCCL send/recv over NVLink on GPUs; the
+CPU test tier runs the same code over gloo).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_tracks(n_tracks: int, rank: int, world: int) -> List[int]:
+    """Round-robin deal of independent tracks to ranks (BASELINE.json configs[4])."""
+    return list(range(rank, n_tracks, world))
+
+
+def slice_partition(n_slices: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, near-equal slice ranges [k0, k1) per rank."""
+    if n_slices < world:
+        raise ValueError(f"cannot split {n_slices} slices over {world} ranks")
+    cuts = [(i * n_slices) // world for i in range(world + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def owned_samples(k0: int, k1: int, hop: int, total: int) -> Tuple[int, int]:
+    """Sample range [lo, hi) of the hops [k0, k1) clipped to the signal length."""
+    return min(total, k0 * hop), min(total, k1 * hop)
+
+
+class SliceShardedSliCQT:
+    """Slice-range sharded analysis / synthesis of one long signal (BASELINE.json configs[3])."""
+
+    def __init__(self, nsgt, total_samples: int, group=None):
+        self.nsgt = nsgt                      # xumx_slicq_b200.nsgt.NSGT_sliced
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.total = int(total_samples)
+        self.hop = nsgt.sl_len // 2
+        self.S = nsgt.n_slices(self.total)
+        self.k0, self.k1 = slice_partition(self.S, self.world)[self.rank]
+        self.lo, self.hi = owned_samples(self.k0, self.k1, self.hop, self.total)
+
+    # -- helpers --------------------------------------------------------------------------
+    def _peer(self, r: int) -> int:
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def _exchange(self, send_to: int | None, send_buf, recv_from: int | None, recv_buf):
+        ops = []
+        if send_to is not None:
+            ops.append(dist.P2POp(dist.isend, send_buf, self._peer(send_to), self.group))
+        if recv_from is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_buf, self._peer(recv_from), self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def local_input(self, x_full: torch.Tensor) -> torch.Tensor:
+        """This rank's owned samples of a full signal [rows, total] (test / single-host helper)."""
+        return x_full[:, self.lo:self.hi].contiguous()
+
+    # -- analysis -------------------------------------------------------------------------
+    def forward(self, x_local: torch.Tensor) -> List[torch.Tensor]:
+        """x_local [rows, hi-lo] (owned samples) -> coefficient buckets [rows, F_b, k1-k0, M_b]."""
+        rows = x_local.shape[0]
+        hop = self.hop
+        right = self.rank + 1 if self.rank + 1 < self.world else None
+        left = self.rank - 1 if self.rank > 0 else None
+        send = None
+        if right is not None:                 # my last hop of input, zero padded past the signal end
+            send = torch.zeros(rows, hop, dtype=torch.float32, device=x_local.device)
+            a = (self.k1 - 1) * hop
+            n = max(0, min(self.hi, a + hop) - a)
+            if n:
+                send[:, :n] = x_local[:, a - self.lo: a - self.lo + n]
+        halo = torch.empty(rows, hop, dtype=torch.float32, device=x_local.device) if left is not None else None
+        self._exchange(right, send, left, halo)
+        if left is None:
+            x_ext, t0 = x_local, 0
+        else:
+            x_ext, t0 = torch.cat((halo, x_local.to(torch.float32)), dim=1), (self.k0 - 1) * hop
+        return self.nsgt.forward_rows(x_ext, k0=self.k0, n_slices=self.k1 - self.k0, t0=t0)
+
+    # -- synthesis ------------------------------------------------------------------------
+    def inverse(self, coefs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """coefficient buckets of slices [k0, k1) -> this rank's owned samples [rows, hi-lo]."""
+        rows = coefs[0].shape[0]
+        hop = self.hop
+        dev = coefs[0].device
+        left = self.rank - 1 if self.rank > 0 else None
+        right = self.rank + 1 if self.rank + 1 < self.world else None
+        halo_out = torch.zeros(rows, hop, dtype=torch.float32, device=dev) if left is not None else None
+        y = self.nsgt.backward_rows(coefs, self.hi - self.lo, k0=self.k0, t0=self.k0 * hop, halo_out=halo_out)
+        halo_in = torch.empty(rows, hop, dtype=torch.float32, device=dev) if right is not None else None
+        self._exchange(left, halo_out, right, halo_in)
+        if right is not None:
+            a = (self.k1 - 1) * hop - self.lo       # start of my last hop inside y
+            n = max(0, y.shape[1] - a)
+            if n:
+                y[:, a:a + n] += halo_in[:, :n]
+        return y
