@@ -229,3 +229,20 @@ def test_error_paths(base, dev):
         base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64, device=dev)], 100)
     with pytest.raises(ValueError):      # a Bark configuration whose slice length has no compiled kernel
         NSGTBase("bark", 100, 50.0, device=dev).nsgt.plan()
+
+
+def test_transform_stream_matches_direct_calls(base, dev):
+    """pipeline.TransformStream only reschedules (H2D / kernels / D2H on three streams): same bits."""
+    from xumx_slicq_b200 import make_filterbanks
+    from xumx_slicq_b200.pipeline import TransformStream
+    nsgt, insgt = make_filterbanks(base)
+    T = 100000
+    hosts = [(torch.rand(2, 2, T) * 2 - 1).pin_memory() for _ in range(5)]
+    model = lambda X: [torch.stack([Xb, 0.5 * Xb]) for Xb in X]
+    ts = TransformStream(base, model, dev)
+    outs = [y.clone() for y in ts.process(iter(hosts))]
+    assert len(outs) == 5
+    for xh, yo in zip(hosts, outs):
+        ref = insgt(model(nsgt(xh.to(dev))), T).cpu()
+        assert yo.shape == (2, 2, 2, T)
+        assert torch.equal(yo, ref)
