@@ -94,6 +94,17 @@ int slicq_inverse(const slicq_plan* plan, const slicq_bucket_view* buckets, int6
                   int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
                   int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Synthesis fused with the realtime model's mask * mixture recombination (reference: Y_t =
+ * mask_t * |X| * (cos, sin)(angle X) == mask_t * X, phase.py:96-113 called from model.py:258-265):
+ * mix[b] holds the MIXTURE coefficients (n_rows rows), masks[b] an fp32 tensor with the logical shape
+ * [n_targets * n_rows][F_b][S][M_b] (element strides in floats, M contiguous).  Output row
+ * t * n_rows + r = synthesis of masks[t * n_rows + r] * mix[r]; y has n_targets * n_rows rows.
+ * The four target coefficient sets are never materialised (24 instead of 32 bytes per coefficient). */
+int slicq_inverse_masked(const slicq_plan* plan, const slicq_bucket_view* mix, const slicq_bucket_view* masks,
+                         int64_t n_targets, int64_t n_rows, int64_t n_slices, int64_t k0, float* y,
+                         int64_t y_row_stride, int64_t length, int64_t t0, float* halo_out, void* scratch,
+                         size_t scratch_bytes, void* stream);
+
 /* number of kernel launches issued by this library since load (bench bookkeeping) */
 int64_t slicq_launch_count(void);
 

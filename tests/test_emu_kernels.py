@@ -152,3 +152,17 @@ def test_errors(base, emu):
         make_filterbanks(base, sample_rate=48000.0)
     with pytest.raises(ValueError):
         base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64)], 100)
+
+
+def test_masked_inverse_equals_plain_inverse_of_masked_coefficients(base):
+    """synthesis fused with mask * mixture (realtime model)."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    x = torch.from_numpy(common.small_input()[:, :14000]).view(1, 2, -1).contiguous()
+    X = nsgt(x)
+    g = torch.Generator().manual_seed(5)
+    masks = [torch.rand((3,) + tuple(Xb.shape[:-1]), generator=g) for Xb in X]          # [targets,B,C,F,S,M]
+    y_ref = insgt([m.unsqueeze(-1) * Xb.unsqueeze(0) for m, Xb in zip(masks, X)], x.shape[-1])
+    y = insgt.forward_masked(X, masks, x.shape[-1])
+    assert y.shape == y_ref.shape == (3, 1, 2, x.shape[-1])
+    assert torch.equal(y, y_ref)

@@ -246,3 +246,16 @@ def test_transform_stream_matches_direct_calls(base, dev):
         ref = insgt(model(nsgt(xh.to(dev))), T).cpu()
         assert yo.shape == (2, 2, 2, T)
         assert torch.equal(yo, ref)
+
+
+def test_masked_inverse_fused(base, dev):
+    """synthesis fused with the realtime model's mask * mixture."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    x = torch.rand(2, 2, 200000, device=dev) * 2 - 1
+    X = nsgt(x)
+    masks = [torch.rand((4,) + tuple(Xb.shape[:-1]), device=dev) for Xb in X]
+    y_ref = insgt([m.unsqueeze(-1) * Xb.unsqueeze(0) for m, Xb in zip(masks, X)], x.shape[-1])
+    y = insgt.forward_masked(X, masks, x.shape[-1])
+    assert y.shape == (4, 2, 2, x.shape[-1])
+    assert torch.equal(y, y_ref)

@@ -23,7 +23,7 @@ SLICQ_E_SCRATCH = -4
 EXPORTS = (
     "slicq_abi_version", "slicq_last_error", "slicq_plan_create", "slicq_plan_destroy",
     "slicq_plan_n_buckets", "slicq_plan_bucket_info", "slicq_plan_num_slices",
-    "slicq_scratch_bytes", "slicq_forward", "slicq_inverse", "slicq_launch_count",
+    "slicq_scratch_bytes", "slicq_forward", "slicq_inverse", "slicq_inverse_masked", "slicq_launch_count",
     "slicq_profile_enable", "slicq_profile_read",
 )
 KERNEL_NAMES = ("slice_fft_fwd", "bins_fwd", "bins_inv", "slice_fft_inv")
@@ -73,6 +73,10 @@ def _declare(lib: C.CDLL) -> C.CDLL:
     lib.slicq_inverse.argtypes = [C.c_void_p, C.POINTER(BucketViewC), C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.slicq_inverse.restype = C.c_int
+    lib.slicq_inverse_masked.argtypes = [C.c_void_p, C.POINTER(BucketViewC), C.POINTER(BucketViewC), C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.slicq_inverse_masked.restype = C.c_int
     lib.slicq_launch_count.restype = C.c_int64
     lib.slicq_profile_enable.argtypes = [C.c_int]
     lib.slicq_profile_enable.restype = C.c_int
@@ -189,6 +193,14 @@ class Plan:
             self.handle, self._views(views), n_rows, n_slices, k0, C.c_void_p(y_ptr), y_row_stride, length, t0,
             C.c_void_p(halo_ptr) if halo_ptr else None, C.c_void_p(scratch_ptr), scratch_bytes,
             C.c_void_p(stream)))
+
+    def inverse_masked(self, mix_views: Sequence[tuple], mask_views: Sequence[tuple], n_targets: int, n_rows: int,
+                       n_slices: int, k0: int, y_ptr: int, y_row_stride: int, length: int, t0: int, halo_ptr: int,
+                       scratch_ptr: int, scratch_bytes: int, stream: int):
+        _check(self.lib, self.lib.slicq_inverse_masked(
+            self.handle, self._views(mix_views), self._views(mask_views), n_targets, n_rows, n_slices, k0,
+            C.c_void_p(y_ptr), y_row_stride, length, t0, C.c_void_p(halo_ptr) if halo_ptr else None,
+            C.c_void_p(scratch_ptr), scratch_bytes, C.c_void_p(stream)))
 
     def launch_count(self) -> int:
         return int(self.lib.slicq_launch_count())

@@ -24,6 +24,18 @@
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
 
+// optional per-phase timing (tuning builds only, -DSLICQ_PHASE_TIMING): thread 0 of every CTA stores
+// clock64() at the phase boundaries into a buffer registered with slicq_debug_set_timing()
+// (tools/phase_timing.py).  Compiled out of the product build.
+#if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
+__device__ long long* g_phase_buf = nullptr;
+#define PHASE_MARK(i) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+extern "C" int slicq_debug_set_timing(long long* buf) { return (int)cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof buf); }
+#else
+#define PHASE_MARK(i) do {} while (0)
+extern "C" int slicq_debug_set_timing(long long*) { return -1; }
+#endif
+
 #ifndef SLICQ_SLICE_THREADS
 #define SLICQ_SLICE_THREADS 384
 #endif
@@ -64,6 +76,7 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
         rdft_sym<P1>(x, base, SA * 2);
     }
     __syncthreads();
+    PHASE_MARK(2);
     // ---- pass B: lane <-> kk (row pair), pitch SA odd
     constexpr int H1 = (P1 - 1) / 2;
     for (int t = threadIdx.x; t < (H1 + 1) * P3; t += blockDim.x) {
@@ -97,6 +110,7 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
         }
     }
     __syncthreads();
+    PHASE_MARK(3);
     // ---- pass C: lane <-> a, pitch SA odd
     for (int t = threadIdx.x; t < P1 * P2; t += blockDim.x) {
         const int b = t / P1, a = t - b * P1;
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     const int rs = p.rs0 + rsl;
     const int row = rs / p.S, k = rs - row * p.S;
     const long long s0 = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;  // x index of slice sample 0
+    PHASE_MARK(0);
     const float* __restrict__ xr = p.x + row * p.x_row_stride;
     const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
     const unsigned short* __restrict__ pin = p.t.perm_in;
@@ -143,6 +158,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
         const int ee = e < e_lo ? e : e + (e_hi - e_lo);
         Z[__ldg(pin + ee)] = make_float2(0.f, 0.f);
     }
+    PHASE_MARK(7);
     const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;   // x range touched by the window support
     const bool interior = sa >= 0 && sb <= p.T;
     const bool vec = ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
@@ -173,8 +189,11 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             Z[__ldg(pin + e)] = make_float2(a, b);
         }
     }
+    PHASE_MARK(4);
     __syncthreads();
+    PHASE_MARK(1);
     pfa_passes<PF, false>(Z);
+    PHASE_MARK(5);
     // even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O); mirrored margins for the bins
     // that reach below DC / above Nyquist (Hermitian symmetry of a real slice)
     float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
@@ -211,6 +230,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             }
         }
     }
+    PHASE_MARK(6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,6 +248,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const int rs = p.rs0 + rsl;
     const int row = rs / p.S, k = rs - row * p.S;
     if ((k & 1) != p.parity) return;
+    PHASE_MARK(0);
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
     const unsigned short* __restrict__ pin = p.t.perm_in;
     constexpr int UG = 2;
@@ -266,7 +287,9 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
         }
     }
     __syncthreads();
+    PHASE_MARK(1);
     pfa_passes<PF, true>(Z);
+    PHASE_MARK(5);
     const float scale = 1.0f / (float)(2 * N);
     const unsigned short* __restrict__ pout = p.t.perm_out;
     // slice sample p = 2n, 2n+1 goes to y index tb + p;  first half (n < N/2) = hop k-1, second = hop k
@@ -311,6 +334,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             }
         }
     }
+    PHASE_MARK(6);
 }
 
 // host-side helpers / launchers ---------------------------------------------------------------

@@ -250,7 +250,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
             return fail(SLICQ_E_UNSUPPORTED, "bucket has too many bins for one CTA");
         }
         b.gt = gt;
-        const int sm = b.n_bins * gt * b.smem_per_fft + 2048;   // + SLICQ_SLOT_BYTES
+        const int sm = b.n_bins * gt * b.smem_per_fft + 4096;   // + SLICQ_SLOT_BYTES
         if (sm > p->bins_smem) p->bins_smem = sm;
         // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
         b.cost = (double)b.n_bins * b.M * (log2((double)b.M) + (f->kind == 3 ? 0.12 * f->A : 0.0) + 4.0);
@@ -384,7 +384,8 @@ extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64
 }
 
 namespace {
-int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqBinsParams& bp, int n_rs) {
+int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqBinsParams& bp, int n_rs,
+                     const slicq_bucket_view* masks = nullptr) {
     int jobs = 0;
     bp.n_buckets = (int)p->buckets.size();
     double total = 0.0;
@@ -395,6 +396,8 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
         a.ptr = reinterpret_cast<float2*>(views[i].ptr);
         a.s_row = views[i].s_row; a.s_bin = views[i].s_bin; a.s_slice = views[i].s_slice;
         a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.gt = b.gt; a.tw_off = b.tw_off;
+        a.mptr = masks ? reinterpret_cast<const float*>(masks[i].ptr) : nullptr;
+        a.ms_row = masks ? masks[i].s_row : 0; a.ms_bin = masks ? masks[i].s_bin : 0; a.ms_slice = masks ? masks[i].s_slice : 0;
         if (p->only_bucket >= 0 && (int)i != p->only_bucket) {       // tuning aid: time one bucket alone
             a.units_per_job = b.gt; a.n_jobs = 0; a.job_start = jobs;
             continue;
@@ -453,9 +456,12 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
     return SLICQ_OK;
 }
 
-extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* buckets, int64_t n_rows,
-                             int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
-                             int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream) {
+namespace {
+// n_rows = output rows; masks == nullptr: plain synthesis of `buckets` (n_rows rows);
+// else buckets hold the mixture (x_rows rows) and masks the per-output-row fp32 masks.
+int inverse_impl(const slicq_plan* p, const slicq_bucket_view* buckets, const slicq_bucket_view* masks, int64_t x_rows,
+                 int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
+                 int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream) {
     if (!p || !y || !buckets) return fail(SLICQ_E_INVALID, "null argument");
     if (n_rows <= 0 || n_slices <= 0 || length < 0) return fail(SLICQ_E_INVALID, "bad shape");
     if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
@@ -471,6 +477,7 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
     (void)nu;
     SlicqBinsParams* bp = new SlicqBinsParams();
     bp->t = p->dev; bp->spec = T; bp->spec_stride = p->sum_M; bp->S = (int)n_slices;
+    bp->x_rows = masks ? (int)x_rows : 0;
     SlicqSliceParams sp;
     memset(&sp, 0, sizeof sp);
     sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->sum_M; sp.S = (int)n_slices;
@@ -482,7 +489,7 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
         // hops that the even slice has to have stored first (see slice_fft_inv_kernel)
         while (n > 1 && u0 + n < units && ((u0 + n) % n_slices) != 0 && (((u0 + n) % n_slices) & 1) == 0) --n;
         bp->n_rs = (int)n; bp->rs0 = (int)u0;
-        const int jobs = fill_bins_params(p, buckets, *bp, (int)n);
+        const int jobs = fill_bins_params(p, buckets, *bp, (int)n, masks);
         { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 1, s); }
         ++g_launches;
         if (rc) break;
@@ -503,3 +510,23 @@ extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* bucke
     }
     return SLICQ_OK;
 }
+}  // namespace
+
+extern "C" int slicq_inverse(const slicq_plan* p, const slicq_bucket_view* buckets, int64_t n_rows,
+                             int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
+                             int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream) {
+    return inverse_impl(p, buckets, nullptr, 0, n_rows, n_slices, k0, y, y_row_stride, length, t0, halo_out,
+                        scratch, scratch_bytes, stream);
+}
+
+extern "C" int slicq_inverse_masked(const slicq_plan* p, const slicq_bucket_view* mix, const slicq_bucket_view* masks,
+                                    int64_t n_targets, int64_t n_rows, int64_t n_slices, int64_t k0, float* y,
+                                    int64_t y_row_stride, int64_t length, int64_t t0, float* halo_out, void* scratch,
+                                    size_t scratch_bytes, void* stream) {
+    if (!masks || n_targets <= 0) return fail(SLICQ_E_INVALID, "masks / n_targets missing");
+    if (p) for (size_t i = 0; i < p->buckets.size(); ++i)
+        if (!masks[i].ptr) return fail(SLICQ_E_INVALID, "null mask pointer");
+    return inverse_impl(p, mix, masks, n_rows, n_targets * n_rows, n_slices, k0, y, y_row_stride, length, t0, halo_out,
+                        scratch, scratch_bytes, stream);
+}
+

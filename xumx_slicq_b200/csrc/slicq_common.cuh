@@ -123,6 +123,10 @@ struct SlicqBucketArg {
     int job_start;        // first job (CTA) index of this bucket inside the launch
     int n_jobs;           // CTAs working on this bucket
     int units_per_job;    // multiple of gt
+    // fused mask*mix synthesis (slicq_inverse_masked): fp32 mask of the same logical shape as the
+    // OUTPUT rows [targets*rows][F][S][M]; null = plain synthesis
+    const float* mptr;
+    long long ms_row, ms_bin, ms_slice;
 };
 
 struct SlicqBinsParams {
@@ -133,6 +137,8 @@ struct SlicqBinsParams {
     int rs0;               // flattened index (row * S + slice) of the first unit of the chunk
     int S;                 // slices per row in this call
     int n_buckets;
+    int x_rows;            // masked synthesis: rows of the mixture tensor (output row r reads mixture row r % x_rows); else 0
+    int pad_;
     SlicqBucketArg b[SLICQ_MAX_BUCKETS];
 };
 

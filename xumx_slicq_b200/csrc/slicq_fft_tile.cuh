@@ -25,6 +25,7 @@ struct JobCtx {
     int gt;         // units per iteration
     int first_bin;
     int rs0, S;     // chunk origin and slices per row: unit g is (row, k) = divmod(rs0 + g, S)
+    int x_rows;     // masked synthesis: mixture rows (0 = plain)
 };
 
 SLICQ_DEVFN float2 cneg_if(float2 v, bool neg) { return neg ? make_float2(-v.x, -v.y) : v; }
@@ -32,15 +33,20 @@ SLICQ_DEVFN float2 cneg_if(float2 v, bool neg) { return neg ? make_float2(-v.x, 
 // The first SLOT_BYTES of a job's shared memory hold, for the units of the current iteration, the
 // element offset of (row, bin f, slice k, 0) in the caller's bucket tensor: slot = gs * F + f.
 // One integer division per slot and iteration instead of one per coefficient.
-#define SLICQ_SLOT_BYTES 2048
+// In masked synthesis (mixture * mask fused into the load, reference: phase.py:96-113 /
+// model.py:258-265) a second table [256, 512) holds the offsets into the mask tensor.
+#define SLICQ_SLOT_BYTES 4096
 SLICQ_DEVFN void fill_slot_off(long long* so, const SlicqBucketArg& b, const JobCtx& j, int base, int ng) {
     for (int t = threadIdx.x; t < ng * j.F; t += blockDim.x) {
         const int gs = t / j.F, f = t - gs * j.F;
         const int rs = j.rs0 + base + gs;
         const int row = rs / j.S, k = rs - row * j.S;
-        so[t] = row * b.s_row + f * b.s_bin + k * b.s_slice;
+        const int rowx = j.x_rows ? row % j.x_rows : row;
+        so[t] = rowx * b.s_row + f * b.s_bin + k * b.s_slice;
+        if (j.x_rows) so[256 + t] = row * b.ms_row + f * b.ms_bin + k * b.ms_slice;
     }
 }
+SLICQ_DEVFN float2 cscale(float2 v, float s) { return make_float2(v.x * s, v.y * s); }
 
 // =========================================================================================
 // kind 1
@@ -109,9 +115,16 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
         __syncthreads();
-        for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
-            const int slot = t / M, n = t - slot * M;
-            sm[slot * PITCH + n] = b.ptr[so[slot] + n];
+        if (b.mptr == nullptr) {
+            for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
+                const int slot = t / M, n = t - slot * M;
+                sm[slot * PITCH + n] = b.ptr[so[slot] + n];
+            }
+        } else {
+            for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
+                const int slot = t / M, n = t - slot * M;
+                sm[slot * PITCH + n] = cscale(b.ptr[so[slot] + n], b.mptr[so[256 + slot] + n]);
+            }
         }
         __syncthreads();
         const int g = base + gs;
@@ -220,10 +233,16 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
         if (act1 && g < j.u1) {
             const int rs = j.rs0 + g;
             const int row = rs / j.S, k = rs - row * j.S;
-            const float2* src = b.ptr + row * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
+            const int rowx = j.x_rows ? row % j.x_rows : row;
+            const float2* src = b.ptr + rowx * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
             float2 v[A];
 #pragma unroll
             for (int n1 = 0; n1 < A; ++n1) v[n1] = cneg_if(src[B * n1], odd != (((B * n1) & 1) != 0));  // (-1)^(B n1 + n2)
+            if (b.mptr != nullptr) {
+                const float* msrc = b.mptr + row * b.ms_row + f1 * b.ms_bin + k * b.ms_slice + n2;
+#pragma unroll
+                for (int n1 = 0; n1 < A; ++n1) v[n1] = cscale(v[n1], msrc[B * n1]);
+            }
             dft<A, false>(v);
             y1[0] = v[0];
 #pragma unroll
@@ -332,6 +351,11 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             float2 v[R];
 #pragma unroll
             for (int n1 = 0; n1 < R; ++n1) v[n1] = cneg_if(src[P * n1], odd != ((n1 & 1) != 0));  // (-1)^(P n1 + n2)
+            if (b.mptr != nullptr) {
+                const float* msrc = b.mptr + so[256 + slot] + n2;
+#pragma unroll
+                for (int n1 = 0; n1 < R; ++n1) v[n1] = cscale(v[n1], msrc[P * n1]);
+            }
             dft<R, false>(v);
 #pragma unroll
             for (int k1 = 0; k1 < R; ++k1) {

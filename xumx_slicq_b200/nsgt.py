@@ -220,6 +220,47 @@ class NSGT_sliced(torch.nn.Module):
         del keep
         return y
 
+    def backward_rows_masked(self, mix: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], length: int,
+                             k0: int = 0, t0: int = 0, halo_out: torch.Tensor | None = None) -> torch.Tensor:
+        """Synthesis fused with mask * mixture (realtime model, phase.py:96-113 / model.py:258-265).
+
+        mix: per bucket complex [N, F_b, S, M_b]; masks: per bucket float32 [T, N, F_b, S, M_b].
+        Returns [T * N, length] (row t * N + n) = inverse of masks[t, n] * mix[n], bitwise equal to
+        ``backward_rows([ (m * x).flatten(0, 1) ])`` without materialising the T coefficient sets."""
+        t = self.tables
+        if len(mix) != len(t.buckets) or len(masks) != len(t.buckets):
+            raise ValueError(f"expected {len(t.buckets)} buckets")
+        c0 = mix[0]
+        _BACKEND.check(c0)
+        N, S = c0.shape[0], c0.shape[2]
+        Tn = masks[0].shape[0]
+        vx, vm, keep = [], [], []
+        for c, m, (_, nb, M) in zip(mix, masks, t.buckets):
+            if c.dtype != torch.complex64:
+                c = c.to(torch.complex64)
+            if tuple(c.shape) != (N, nb, S, M) or tuple(m.shape) != (Tn, N, nb, S, M):
+                raise ValueError(f"bucket shapes {tuple(c.shape)}, {tuple(m.shape)} != {(N, nb, S, M)}, {(Tn, N, nb, S, M)}")
+            if c.stride(3) != 1:
+                c = c.contiguous()
+            m = m.to(torch.float32).reshape(Tn * N, nb, S, M)
+            if m.stride(3) != 1:
+                m = m.contiguous()
+            keep += [c, m]
+            vx.append(self._view_of(c))
+            vm.append(self._view_of(m))
+        length = int(length)
+        out_len = max(0, min(length, (int(k0) + S) * t.hop - int(t0)))
+        plan = self.plan(c0.device)
+        with _BACKEND.device_guard(c0.device):
+            y = torch.empty((Tn * N, out_len), dtype=torch.float32, device=c0.device)
+            nbytes = plan.scratch_bytes(Tn * N, S, True)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=c0.device)
+            plan.inverse_masked(vx, vm, Tn, N, S, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len,
+                                int(t0), halo_out.data_ptr() if halo_out is not None else 0,
+                                scratch.data_ptr(), nbytes, _BACKEND.stream(c0.device))
+        del keep
+        return y
+
     def backward(self, cseq: Sequence[torch.Tensor], length: int) -> torch.Tensor:
         """slicq.py:198-230: list of [S, N, F_b, M_b] complex -> [N, length].
         Unlike the reference this does not modify ``cseq`` in place."""

@@ -124,6 +124,29 @@ class INSGT_SL(nn.Module):
         return y.view(*lead, -1)
 
 
+    def forward_masked(self, X_list, mask_list, length: int) -> Tensor:
+        """Fused realtime-model synthesis (not in the reference API):
+        X_list per bucket [B, C, F, S, M, 2] (the mixture sliCQT), mask_list per bucket
+        [targets, B, C, F, S, M] (the CDAE sigmoid masks, model.py:231-234).  Returns
+        [targets, B, C, length] == self.forward([m.unsqueeze(-1) * X for ...], length)."""
+        dev = _module_device(self.nsgt)
+        xs, ms = [], []
+        lead = None
+        for X, Mk in zip(X_list, mask_list):
+            if X.device != dev and X.device.type == "cpu":
+                X, Mk = X.to(dev), Mk.to(dev)
+            if X.dtype != torch.float32:
+                X = X.to(torch.float32)
+            if X.stride(-1) != 1 or X.stride(-2) != 2:
+                X = X.contiguous()
+            Xc = torch.view_as_complex(X)
+            lead = tuple(Xc.shape[:-3])
+            xs.append(Xc.reshape((-1,) + tuple(Xc.shape[-3:])))
+            ms.append(Mk.reshape((Mk.shape[0], -1) + tuple(Mk.shape[-3:])))
+        y = self.nsgt.nsgt.backward_rows_masked(xs, ms, length)
+        return y.view(ms[0].shape[0], *lead, -1)
+
+
 class ComplexNorm(nn.Module):
     """Magnitude of a ragged sliCQT list or a single tensor (transforms.py:181-208)."""
 
