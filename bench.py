@@ -230,6 +230,7 @@ def main():
         }))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banners go to stderr: stdout carries ONE JSON line
     import torch
     import torch.distributed as dist
     from xumx_slicq_b200 import NSGTBase, make_filterbanks, _cabi
