@@ -87,6 +87,13 @@ int slicq_forward(const slicq_plan* plan, const float* x, int64_t n_rows, int64_
                   int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
                   const slicq_bucket_view* buckets, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Same as slicq_forward for the canonical packed layout: `coefs` is ONE allocation of
+ * n_rows * n_slices * sum(M_j) complex64 in which bucket b is the contiguous block
+ * [n_rows][F_b][n_slices][M_b], buckets in order (what the Python wrappers allocate). */
+int slicq_forward_packed(const slicq_plan* plan, const float* x, int64_t n_rows, int64_t x_row_stride,
+                         int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
+                         void* scratch, size_t scratch_bytes, void* stream);
+
 /* Synthesis.  y: [n_rows] rows, row r at y + r*y_row_stride, receives `length` samples whose
  * first one is global sample t0.  halo_out (optional, [n_rows][hop] float32) receives the part of
  * local slice 0 that belongs to the hop before this shard (only when k0 > 0). */

@@ -18,3 +18,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The GPU tier needs the in-tree libslicq.so; build it (nvcc, sm_100a) if a fresh checkout lacks it."""
+    lib = os.path.join(ROOT, "xumx_slicq_b200", "libslicq.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+    yield

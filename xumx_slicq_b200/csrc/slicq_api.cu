@@ -456,6 +456,24 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
     return SLICQ_OK;
 }
 
+// Canonical packed layout: all buckets in one allocation, bucket b = contiguous [n_rows][F_b][S][M_b].
+extern "C" int slicq_forward_packed(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                                    int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
+                                    void* scratch, size_t scratch_bytes, void* stream) {
+    if (!p || !coefs) return fail(SLICQ_E_INVALID, "null argument");
+    std::vector<slicq_bucket_view> v(p->buckets.size());
+    unsigned char* base = reinterpret_cast<unsigned char*>(coefs);
+    for (size_t i = 0; i < p->buckets.size(); ++i) {
+        const Bucket& b = p->buckets[i];
+        v[i].ptr = base;
+        v[i].s_slice = b.M;
+        v[i].s_bin = (int64_t)n_slices * b.M;
+        v[i].s_row = (int64_t)b.n_bins * n_slices * b.M;
+        base += (size_t)n_rows * b.n_bins * n_slices * b.M * 8;
+    }
+    return slicq_forward(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(), scratch, scratch_bytes, stream);
+}
+
 namespace {
 // n_rows = output rows; masks == nullptr: plain synthesis of `buckets` (n_rows rows);
 // else buckets hold the mixture (x_rows rows) and masks the per-output-row fp32 masks.

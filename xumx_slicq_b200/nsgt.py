@@ -139,14 +139,25 @@ class NSGT_sliced(torch.nn.Module):
     def n_slices(self, n_samples: int) -> int:
         return self.tables.num_slices(int(n_samples))
 
-    def alloc_coefficients(self, n_rows: int, n_slices: int, device) -> tuple:
-        """One slab for all buckets; returns (slab, [bucket tensors [N,F,S,M] complex64])."""
+    def alloc_coefficients(self, n_rows: int, n_slices: int, device, lead=None, as_real: bool = False) -> tuple:
+        """One slab for all buckets (canonical packed layout of include/slicq.h).  Returns
+        (slab, [bucket tensors]); buckets are complex64 [N,F,S,M] or, with ``as_real``, float32
+        [*lead,F,S,M,2] views -- ONE as_strided per bucket (host overhead matters at small batch)."""
         t = self.tables
-        slab = torch.empty(n_rows * n_slices * t.sum_M, dtype=torch.complex64, device=device)
+        slab = torch.empty(n_rows * n_slices * t.sum_M * 2, dtype=torch.float32, device=device)
         out, o = [], 0
+        lead = tuple(lead) if lead is not None else (n_rows,)
         for (_, nb, M) in t.buckets:
-            n = n_rows * nb * n_slices * M
-            out.append(slab[o:o + n].view(n_rows, nb, n_slices, M))
+            n = n_rows * nb * n_slices * M * 2
+            inner = (nb * n_slices * M * 2, n_slices * M * 2, M * 2, 2, 1)           # strides of [N,F,S,M,2]
+            if as_real:
+                st, acc = [], nb * n_slices * M * 2
+                for d in reversed(lead):
+                    st.append(acc)
+                    acc *= d
+                out.append(slab.as_strided(lead + (nb, n_slices, M, 2), tuple(reversed(st)) + inner[1:], o))
+            else:
+                out.append(torch.view_as_complex(slab.as_strided((n_rows, nb, n_slices, M, 2), inner, o)))
             o += n
         return slab, out
 
@@ -156,7 +167,8 @@ class NSGT_sliced(torch.nn.Module):
         return (c.data_ptr(), c.stride(0), c.stride(1), c.stride(2))
 
     # -- analysis ---------------------------------------------------------------------------
-    def forward_rows(self, x: torch.Tensor, k0: int = 0, n_slices: int | None = None, t0: int = 0) -> List[torch.Tensor]:
+    def forward_rows(self, x: torch.Tensor, k0: int = 0, n_slices: int | None = None, t0: int = 0,
+                     lead=None, as_real: bool = False) -> List[torch.Tensor]:
         """x [N, T] float32 -> list of contiguous [N, F_b, S, M_b] complex64 (canonical layout).
 
         ``k0 / n_slices / t0`` select a slice range of a longer signal (shard of a long track):
@@ -172,12 +184,11 @@ class NSGT_sliced(torch.nn.Module):
         S = self.n_slices(T) if n_slices is None else int(n_slices)
         plan = self.plan(x.device)
         with _BACKEND.device_guard(x.device):
-            slab, out = self.alloc_coefficients(N, S, x.device)
+            slab, out = self.alloc_coefficients(N, S, x.device, lead=lead, as_real=as_real)
             nbytes = plan.scratch_bytes(N, S, False)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            plan.forward(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S,
-                         [self._view_of(c) for c in out], scratch.data_ptr(), nbytes,
-                         _BACKEND.stream(x.device))
+            plan.forward_packed(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S, slab.data_ptr(),
+                                scratch.data_ptr(), nbytes, _BACKEND.stream(x.device))
         return out
 
     def forward(self, sig: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -259,6 +270,27 @@ class NSGT_sliced(torch.nn.Module):
                                 int(t0), halo_out.data_ptr() if halo_out is not None else 0,
                                 scratch.data_ptr(), nbytes, _BACKEND.stream(c0.device))
         del keep
+        return y
+
+    @staticmethod
+    def _BACKEND_check(t: torch.Tensor):
+        _BACKEND.check(t)
+
+    def backward_views(self, views, n_rows: int, n_slices: int, device, length: int, k0: int = 0, t0: int = 0,
+                       halo_out: torch.Tensor | None = None) -> torch.Tensor:
+        """Synthesis from precomputed (ptr, s_row, s_bin, s_slice) bucket views (complex64 element
+        strides); the caller keeps the tensors alive and guarantees shapes / 16-byte alignment."""
+        t = self.tables
+        length = int(length)
+        out_len = max(0, min(length, (int(k0) + n_slices) * t.hop - int(t0)))
+        plan = self.plan(device)
+        with _BACKEND.device_guard(device):
+            y = torch.empty((n_rows, out_len), dtype=torch.float32, device=device)
+            nbytes = plan.scratch_bytes(n_rows, n_slices, True)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            plan.inverse(views, n_rows, n_slices, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len,
+                         int(t0), halo_out.data_ptr() if halo_out is not None else 0,
+                         scratch.data_ptr(), nbytes, _BACKEND.stream(device))
         return y
 
     def backward(self, cseq: Sequence[torch.Tensor], length: int) -> torch.Tensor:

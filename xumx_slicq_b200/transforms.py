@@ -86,9 +86,7 @@ class NSGT_SL(nn.Module):
         if x.device != dev and x.device.type == "cpu":
             x = x.to(dev)
         x = x.contiguous().view(-1, shape[-1])
-        C = self.nsgt.nsgt.forward_rows(x)
-        lead = tuple(shape[:-1])
-        return [torch.view_as_real(c).view(lead + tuple(c.shape[1:]) + (2,)) for c in C]
+        return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True)
 
 
 class INSGT_SL(nn.Module):
@@ -104,6 +102,26 @@ class INSGT_SL(nn.Module):
 
     def forward(self, X_list, length: int) -> Tensor:
         dev = _module_device(self.nsgt)
+        nsg = self.nsgt.nsgt
+        buckets = nsg.tables.buckets
+        if len(X_list) == len(buckets) and all(
+                X.is_contiguous() and X.dtype == torch.float32 and X.device == dev for X in X_list):
+            # fast path (model outputs, forward outputs): bucket views straight from the real tensors,
+            # no per-bucket view_as_complex / reshape on the host
+            X0 = X_list[0]
+            lead = tuple(X0.shape[:-4])
+            S = X0.shape[-3]
+            rows = 1
+            for d in lead:
+                rows *= d
+            views = []
+            for X, (_, nb, M) in zip(X_list, buckets):
+                if tuple(X.shape) != lead + (nb, S, M, 2):
+                    raise ValueError(f"bucket shape {tuple(X.shape)} != {lead + (nb, S, M, 2)}")
+                views.append((X.data_ptr(), nb * S * M, S * M, M))
+            nsg._BACKEND_check(X0)
+            y = nsg.backward_views(views, rows, S, dev, length)
+            return y.view(*lead, -1)
         cs = []
         lead = None
         for X in X_list:
@@ -120,9 +138,8 @@ class INSGT_SL(nn.Module):
             except RuntimeError:                      # leading dims not collapsible: make it so
                 Xc = Xc.contiguous().view((-1,) + tuple(Xc.shape[-3:]))
             cs.append(Xc)
-        y = self.nsgt.nsgt.backward_rows(cs, length)
+        y = nsg.backward_rows(cs, length)
         return y.view(*lead, -1)
-
 
     def forward_masked(self, X_list, mask_list, length: int) -> Tensor:
         """Fused realtime-model synthesis (not in the reference API):
