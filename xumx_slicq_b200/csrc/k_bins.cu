@@ -12,6 +12,12 @@
 // per-launch job table) and owns a contiguous range of (row,slice) units of that bucket.
 #include "slicq_fft_tile.cuh"
 
+#if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
+extern "C" int slicq_debug_set_bins_timing(long long* buf) { return (int)cudaMemcpyToSymbol(g_bins_phase_buf, &buf, sizeof buf); }
+#else
+extern "C" int slicq_debug_set_bins_timing(long long*) { return -1; }
+#endif
+
 namespace {
 
 SLICQ_DEVFN int find_bucket(const SlicqBinsParams& p, int job) {

@@ -19,6 +19,23 @@
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
 
+// optional tuning instrumentation (-DSLICQ_PHASE_TIMING): per-CTA accumulated cycles of the analysis
+// two-pass kernel's phases, written by thread 0 to a buffer registered with
+// slicq_debug_set_bins_timing() (tools/bins_timing.py).  Compiled out of the product build.
+#if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
+__device__ long long* g_bins_phase_buf = nullptr;   // this header is included by k_bins.cu only
+#define BINS_T(v) const long long v = clock64()
+#define BINS_ACC(i, a, b) do { if (threadIdx.x == 0) bins_acc_[i] += (b) - (a); } while (0)
+#define BINS_DECL long long bins_acc_[6] = {0, 0, 0, 0, 0, 0}
+#define BINS_FLUSH(M_) do { if (threadIdx.x == 0 && g_bins_phase_buf) { long long* o = g_bins_phase_buf + (long long)blockIdx.x * 8; \
+        for (int q_ = 0; q_ < 6; ++q_) o[q_] = bins_acc_[q_]; o[6] = (M_); o[7] = 1; } } while (0)
+#else
+#define BINS_T(v) do {} while (0)
+#define BINS_ACC(i, a, b) do {} while (0)
+#define BINS_DECL do {} while (0)
+#define BINS_FLUSH(M_) do {} while (0)
+#endif
+
 struct JobCtx {
     int u0, u1;     // unit range of this job (indices local to the chunk)
     int F;          // bins in the bucket
@@ -169,7 +186,9 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
     float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
     const float2* __restrict__ tw = p.t.tw + b.tw_off + 0;
+    BINS_DECL;
     for (int base = j.u0; base < j.u1; base += j.gt) {
+        BINS_T(t0_);
         const int g = base + gs1;
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
@@ -187,7 +206,9 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             for (int k1 = 1; k1 < A; ++k1)
                 y1[k1 * BP] = cneg_if(cmul_conj(v[k1], __ldg(tw + n2 * k1)), k1 & 1);  // (-1)^k1 folded here
         }
+        BINS_T(t1_);
         __syncthreads();
+        BINS_T(t2_);
         for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
             const int slot = t / A, k1 = t - slot * A;
             const float2* src = sm + slot * PER + k1 * BP;
@@ -199,8 +220,12 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
 #pragma unroll
             for (int k2 = 0; k2 < B; ++k2) o[A * k2] = cneg_if(v[k2], (A * k2) & 1);
         }
+        BINS_T(t3_);
         __syncthreads();
+        BINS_T(t4_);
+        BINS_ACC(1, t0_, t1_); BINS_ACC(2, t1_, t2_); BINS_ACC(3, t2_, t3_); BINS_ACC(4, t3_, t4_); BINS_ACC(5, t0_, t4_);
     }
+    BINS_FLUSH(M);
 }
 
 // synthesis: x[B*n1 + n2] -> X[k1 + A*k2];  same shape as the analysis: pass 1 = DFT-A with the
