@@ -148,6 +148,13 @@ struct slicq_plan {
     int target_jobs;      // CTAs per bins launch the job split aims for
     int min_iters;        // ... but a job keeps at least this many iterations (instruction-cache reuse)
     int only_bucket;      // -1, or (SLICQ_ONLY_BUCKET, tuning aid) the single bucket the bins kernels process
+    // Large calls are split by rows into two halves that run on two internal streams (forked from and
+    // joined back into the caller's stream): the memory-latency-bound and the issue-bound kernels of
+    // the two halves overlap on the SMs.  Rows are independent, so the results do not change.
+    long long split_units;          // split when the call has at least this many units (0 = never)
+    mutable cudaStream_t side[2];
+    mutable cudaEvent_t ev_fork, ev_join[2];
+    mutable bool side_ready;
 };
 
 extern "C" int slicq_abi_version(void) { return SLICQ_ABI_VERSION; }
@@ -174,6 +181,10 @@ extern "C" int slicq_profile_read(double* ms, int64_t* launches) {
 
 extern "C" void slicq_plan_destroy(slicq_plan* p) {
     if (!p) return;
+    if (p->side_ready) {
+        cudaStreamDestroy(p->side[0]); cudaStreamDestroy(p->side[1]);
+        cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join[0]); cudaEventDestroy(p->ev_join[1]);
+    }
     for (void* q : p->owned) cudaFree(q);
     delete p;
 }
@@ -337,6 +348,9 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     const char* envj = getenv("SLICQ_BINS_JOBS");
     p->target_jobs = envj ? atoi(envj) : 1184;   // 148 SMs x 2-4 resident CTAs x 2-4 waves
     if (p->target_jobs < 1) p->target_jobs = 1;
+    const char* envs = getenv("SLICQ_SPLIT_UNITS");
+    p->split_units = envs ? atoll(envs) : 1184;
+    p->side_ready = false;
     const char* envb = getenv("SLICQ_ONLY_BUCKET");
     p->only_bucket = envb ? atoi(envb) : -1;
     const char* envi = getenv("SLICQ_BINS_MIN_ITERS");
@@ -375,12 +389,32 @@ long long chunk_units(const slicq_plan* p, int inverse) {
 }
 }  // namespace
 
-extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse) {
-    if (!p || n_rows <= 0 || n_slices <= 0) return 0;
-    long long units = n_rows * n_slices;
+namespace {
+bool use_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices) {
+    return p->split_units > 0 && n_rows >= 2 && n_rows * n_slices >= p->split_units;
+}
+size_t half_scratch(const slicq_plan* p, int64_t rows, int64_t n_slices, int inverse) {
+    long long units = rows * n_slices;
     const long long c = chunk_units(p, inverse);
     if (units > c) units = c;
-    return (size_t)(units * bytes_per_unit(p, inverse) + 256);
+    return ((size_t)(units * bytes_per_unit(p, inverse)) + 511) & ~(size_t)255;
+}
+int ensure_side_streams(const slicq_plan* p) {
+    if (p->side_ready) return 0;
+    if (cudaStreamCreateWithFlags(&p->side[0], cudaStreamNonBlocking) || cudaStreamCreateWithFlags(&p->side[1], cudaStreamNonBlocking) ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) || cudaEventCreateWithFlags(&p->ev_join[0], cudaEventDisableTiming) ||
+        cudaEventCreateWithFlags(&p->ev_join[1], cudaEventDisableTiming))
+        return -1;
+    p->side_ready = true;
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse) {
+    if (!p || n_rows <= 0 || n_slices <= 0) return 0;
+    if (use_split(p, n_rows, n_slices))
+        return half_scratch(p, n_rows / 2, n_slices, inverse) + half_scratch(p, n_rows - n_rows / 2, n_slices, inverse) + 256;
+    return half_scratch(p, n_rows, n_slices, inverse) + 256;
 }
 
 namespace {
@@ -416,6 +450,32 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
 }
 }  // namespace
 
+namespace {
+int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                const slicq_bucket_view* buckets, void* scratch, cudaStream_t s);
+int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const slicq_bucket_view* masks, int64_t x_rows,
+                int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
+                int64_t t0, float* halo_out, void* scratch, cudaStream_t s);
+
+// run `fn(half, row0, rows, scratch, stream)` for the two row halves on the plan's side streams
+template <class F>
+int run_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse, void* scratch, cudaStream_t s, F fn) {
+    if (ensure_side_streams(p)) return fail(SLICQ_E_CUDA, "cannot create internal streams");
+    const int64_t ra = n_rows / 2, rb = n_rows - ra;
+    unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+    cudaEventRecord(p->ev_fork, s);
+    int rc = 0;
+    for (int h = 0; h < 2 && rc == 0; ++h) {
+        cudaStreamWaitEvent(p->side[h], p->ev_fork, 0);
+        rc = fn(h == 0 ? 0 : ra, h == 0 ? ra : rb, base + (h == 0 ? 0 : half_scratch(p, ra, n_slices, inverse)), p->side[h]);
+        cudaEventRecord(p->ev_join[h], p->side[h]);
+        cudaStreamWaitEvent(s, p->ev_join[h], 0);
+    }
+    return rc;
+}
+}  // namespace
+
 extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
                              int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
                              const slicq_bucket_view* buckets, void* scratch, size_t scratch_bytes, void* stream) {
@@ -426,7 +486,21 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
         return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
     for (size_t i = 0; i < p->buckets.size(); ++i)
         if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
+    if (use_split(p, n_rows, n_slices)) {
+        return run_split(p, n_rows, n_slices, 0, scratch, s0, [&](int64_t r0, int64_t rows, void* scr, cudaStream_t st) {
+            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size());
+            for (auto& b : v) b.ptr = reinterpret_cast<float2*>(b.ptr) + r0 * b.s_row;
+            return forward_one(p, x + r0 * x_row_stride, rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(), scr, st);
+        });
+    }
+    return forward_one(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, buckets, scratch, s0);
+}
+
+namespace {
+int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                const slicq_bucket_view* buckets, void* scratch, cudaStream_t s) {
     const long long units = n_rows * n_slices, cu = chunk_units(p, 0);
     float2* H = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
     SlicqSliceParams sp;
@@ -455,6 +529,7 @@ extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows
     }
     return SLICQ_OK;
 }
+}  // namespace
 
 // Canonical packed layout: all buckets in one allocation, bucket b = contiguous [n_rows][F_b][S][M_b].
 extern "C" int slicq_forward_packed(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
@@ -487,7 +562,21 @@ int inverse_impl(const slicq_plan* p, const slicq_bucket_view* buckets, const sl
         return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
     for (size_t i = 0; i < p->buckets.size(); ++i)
         if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
+    if (!masks && use_split(p, n_rows, n_slices)) {
+        return run_split(p, n_rows, n_slices, 1, scratch, s0, [&](int64_t r0, int64_t rows, void* scr, cudaStream_t st) {
+            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size());
+            for (auto& b : v) b.ptr = reinterpret_cast<float2*>(b.ptr) + r0 * b.s_row;
+            return inverse_one(p, v.data(), nullptr, 0, rows, n_slices, k0, y + r0 * y_row_stride, y_row_stride, length, t0,
+                               halo_out ? halo_out + r0 * p->hop : nullptr, scr, st);
+        });
+    }
+    return inverse_one(p, buckets, masks, x_rows, n_rows, n_slices, k0, y, y_row_stride, length, t0, halo_out, scratch, s0);
+}
+
+int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const slicq_bucket_view* masks, int64_t x_rows,
+                int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
+                int64_t t0, float* halo_out, void* scratch, cudaStream_t s) {
     const long long units = n_rows * n_slices, cu = chunk_units(p, 1);
     const long long nu = units < cu ? units : cu;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);

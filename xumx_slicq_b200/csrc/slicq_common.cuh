@@ -41,6 +41,14 @@ static inline void __syncthreads() { slicq_emu_sync(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 typedef int cudaError_t;
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline int cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline int cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline int cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
+static inline int cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline int cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
