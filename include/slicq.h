@@ -51,7 +51,15 @@ typedef struct slicq_tables {
     const float* win_fwd;  /* [sum M] analysis windows g_j[m] (peak at m = 0)             */
     const float* win_inv;  /* [sum M] dual windows gd_j[m]                                */
     const float* tukey;    /* [L] slicing window                                          */
+    int32_t flags;         /* SLICQ_PLAN_* bits                                           */
 } slicq_tables;
+
+/* Plan flag: the ANALYSIS entry of this plan computes the adjoint (transpose) of the SYNTHESIS of the
+ * normal plan -- used for autograd through INSGT_SL (the reference gets it from torch autograd on
+ * nsgt/nsigtf.py + nsgt/unslicing.py).  The slice spectrum is scaled by 2/L (1/L at DC / Nyquist) and
+ * bins reaching outside [0, L/2] read zeros instead of the Hermitian mirror; the caller passes
+ * tukey = 1 and win_fwd = gd * M^2. */
+#define SLICQ_PLAN_ADJOINT_OF_SYNTHESIS 1
 
 typedef struct slicq_plan slicq_plan; /* opaque */
 

@@ -166,3 +166,29 @@ def test_masked_inverse_equals_plain_inverse_of_masked_coefficients(base):
     y = insgt.forward_masked(X, masks, x.shape[-1])
     assert y.shape == y_ref.shape == (3, 1, 2, x.shape[-1])
     assert torch.equal(y, y_ref)
+
+
+def test_inverse_autograd_is_the_exact_adjoint(base):
+    """gradients through INSGT_SL.  The transform is linear, so the gradient of
+    L = <S c, g> w.r.t. c must be S^T g: check <S c, g> == <c, S^T g> and a directional derivative."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    T = 14000
+    x = torch.from_numpy(common.small_input()[:, :T]).view(1, 2, -1).contiguous()
+    X = [Xb.clone().requires_grad_(True) for Xb in nsgt(x)]
+    g = torch.randn(1, 2, T, generator=torch.Generator().manual_seed(3))
+    y = insgt(X, T)
+    assert y.requires_grad
+    (y * g).sum().backward()
+    lhs = float((y.detach().double() * g.double()).sum())
+    rhs = float(sum((Xb.detach().double() * Xb.grad.double()).sum() for Xb in X))
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), 1.0), (lhs, rhs)      # <S c, g> == <c, S^T g>
+    # directional derivative along a random direction d: d/de <S(c + e d), g> = <d, S^T g>
+    d = [torch.randn(Xb.shape, generator=torch.Generator().manual_seed(7 + i)) for i, Xb in enumerate(X)]
+    with torch.no_grad():
+        y2 = insgt([Xb.detach() + 0.5 * db for Xb, db in zip(X, d)], T)
+    fd = float(((y2 - y.detach()).double() * g.double()).sum()) / 0.5
+    an = float(sum((db.double() * Xb.grad.double()).sum() for db, Xb in zip(d, X)))
+    assert abs(fd - an) <= 2e-4 * max(abs(an), 1.0), (fd, an)
+    with pytest.raises(NotImplementedError):
+        nsgt(x.clone().requires_grad_(True))

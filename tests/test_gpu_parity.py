@@ -259,3 +259,27 @@ def test_masked_inverse_fused(base, dev):
     y = insgt.forward_masked(X, masks, x.shape[-1])
     assert y.shape == (4, 2, 2, x.shape[-1])
     assert torch.equal(y, y_ref)
+
+
+def test_inverse_autograd_adjoint(base, dev):
+    """Gradients through INSGT_SL (SDR-loss training, training.py:83-95): exact adjoint on the GPU."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    T = 88200
+    x = torch.rand(3, 2, T, device=dev) * 2 - 1
+    X = [Xb.clone().requires_grad_(True) for Xb in nsgt(x)]
+    g = torch.randn(3, 2, T, device=dev)
+    y = insgt(X, T)
+    (y * g).sum().backward()
+    lhs = float((y.detach().double() * g.double()).sum())
+    rhs = float(sum((Xb.detach().double() * Xb.grad.double()).sum() for Xb in X))
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), 1.0), (lhs, rhs)
+    # an SDR-style loss decreases along the negative gradient
+    target = torch.rand(3, 2, T, device=dev) * 2 - 1
+    C = [Xb.detach().clone().requires_grad_(True) for Xb in X]
+    loss0 = ((insgt(C, T) - target) ** 2).mean()
+    loss0.backward()
+    with torch.no_grad():
+        C2 = [c - 200.0 * c.grad for c in C]
+        loss1 = ((insgt(C2, T) - target) ** 2).mean()
+    assert float(loss1) < float(loss0)

@@ -38,6 +38,7 @@ class SlicqTablesC(C.Structure):
         ("win_fwd", C.POINTER(C.c_float)),
         ("win_inv", C.POINTER(C.c_float)),
         ("tukey", C.POINTER(C.c_float)),
+        ("flags", C.c_int32),
     ]
 
 
@@ -150,7 +151,8 @@ class Plan:
             self._keep[1].ctypes.data_as(C.POINTER(C.c_int32)),
             self._keep[2].ctypes.data_as(C.POINTER(C.c_float)),
             self._keep[3].ctypes.data_as(C.POINTER(C.c_float)),
-            self._keep[4].ctypes.data_as(C.POINTER(C.c_float)))
+            self._keep[4].ctypes.data_as(C.POINTER(C.c_float)),
+            int(getattr(tables, "flags", 0)))
         h = C.c_void_p()
         _check(self.lib, self.lib.slicq_plan_create(C.byref(t), C.byref(h)))
         self.handle = h

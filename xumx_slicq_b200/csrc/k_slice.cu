@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
     const unsigned short* __restrict__ pout = p.t.perm_out;
     const int pad_l = p.t.pad_l, pad_r = p.t.pad_r;
+    const float sc = p.t.spec_scale, se = p.t.ends_scale;
+    const float mir = p.t.adjoint ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
     constexpr int UP = 4;
     for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UP * blockDim.x) {
         int pk[UP], pn[UP];
@@ -214,19 +216,19 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             if (kk > N / 2) continue;
             const float2 zk = Z[pk[u]];
             if (kk == 0) {
-                H[0] = make_float2(zk.x + zk.y, 0.f);
-                H[N] = make_float2(zk.x - zk.y, 0.f);
+                H[0] = make_float2((zk.x + zk.y) * se, 0.f);
+                H[N] = make_float2((zk.x - zk.y) * se, 0.f);
             } else {
                 const float2 zn = Z[pn[u]];
                 const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
                 const float2 O = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));  // -(i/2)(zk - conj zn)
                 const float2 t = cmul(wk[u], O);
-                const float2 hk = make_float2(E.x + t.x, E.y + t.y);
-                const float2 hn = make_float2(E.x - t.x, -(E.y - t.y));
+                const float2 hk = make_float2((E.x + t.x) * sc, (E.y + t.y) * sc);
+                const float2 hn = make_float2((E.x - t.x) * sc, -(E.y - t.y) * sc);
                 H[kk] = hk;
                 H[N - kk] = hn;
-                if (kk <= pad_l) H[-kk] = make_float2(hk.x, -hk.y);
-                if (kk <= pad_r) H[N + kk] = make_float2(hn.x, -hn.y);
+                if (kk <= pad_l) H[-kk] = make_float2(hk.x * mir, -hk.y * mir);
+                if (kk <= pad_r) H[N + kk] = make_float2(hn.x * mir, -hn.y * mir);
             }
         }
     }

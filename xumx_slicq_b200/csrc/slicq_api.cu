@@ -324,6 +324,9 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
     d.pad_l = pad_l; d.pad_r = pad_r; d.tw_lo = tw_lo; d.tw_hi = tw_hi;
+    d.adjoint = (t->flags & SLICQ_PLAN_ADJOINT_OF_SYNTHESIS) ? 1 : 0;
+    d.spec_scale = d.adjoint ? (float)(2.0 / L) : 1.f;
+    d.ends_scale = d.adjoint ? (float)(1.0 / L) : 1.f;
     int rc = 0;
     rc |= upload(tuk, &d.tukey, p->owned);
     rc |= upload(wf, &d.wf, p->owned);

@@ -103,6 +103,9 @@ struct SlicqDeviceTables {
     int pad_l;      // spectrum rows carry pad_l mirrored bins below DC ...
     int pad_r;      // ... and pad_r mirrored bins above Nyquist (bins never need reflection logic)
     int tw_lo, tw_hi;       // support of the slicing window: tukey[p] != 0 only for p in [tw_lo, tw_hi)
+    int adjoint;            // 1: analysis kernels compute the adjoint of the synthesis (see include/slicq.h)
+    float spec_scale;       // factor on the slice spectrum (1, or 2/L in adjoint mode) ...
+    float ends_scale;       // ... and on its DC / Nyquist bins (1, or 1/L)
     const float* tukey;     // [L]   slicing window
     // windows are stored in *centred* order m' = m~ + M/2 (m~ in [-M/2, M/2) the offset from pos_j)
     const float* wf;        // [sum_M] analysis windows  g_j * (-1)^(pos_j/2) / M_j

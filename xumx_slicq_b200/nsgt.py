@@ -49,6 +49,20 @@ class _CudaBackend:
 _BACKEND = _CudaBackend()
 
 
+class _AdjointTables:
+    """Tables of the plan whose ANALYSIS entry is the adjoint of the normal plan's SYNTHESIS
+    (include/slicq.h: SLICQ_PLAN_ADJOINT_OF_SYNTHESIS): no slicing window, dual windows * M^2."""
+
+    def __init__(self, t):
+        self.sllen, self.n_bins = t.sllen, t.n_bins
+        self.bin_M, self.bin_pos = t.bin_M, t.bin_pos
+        m2 = np.concatenate([np.full(int(m), float(m) * float(m), dtype=np.float64) for m in t.bin_M])
+        self.win_fwd = (t.win_inv.astype(np.float64) * m2).astype(np.float32)
+        self.win_inv = t.win_inv
+        self.tukey = np.ones(t.sllen, dtype=np.float32)
+        self.flags = 1
+
+
 class _PlanCache:
     """Per-device `slicq_plan` handles, created lazily; never copied (ctypes handles)."""
 
@@ -99,6 +113,8 @@ class NSGT_sliced(torch.nn.Module):
         self.ncoefs = t.ncoefs
         self.nn = self.sl_len
         self._cache = _PlanCache()
+        self._adj_cache = _PlanCache()
+        self._adj_tables = None
         self._anchor = torch.zeros(1, device=self.device) if self.device.type == "cpu" else None
         if self.device.type != "cpu":
             self._anchor = torch.zeros(1, device=self.device)
@@ -292,6 +308,29 @@ class NSGT_sliced(torch.nn.Module):
                          int(t0), halo_out.data_ptr() if halo_out is not None else 0,
                          scratch.data_ptr(), nbytes, _BACKEND.stream(device))
         return y
+
+    # -- adjoint of the synthesis (autograd through the inverse transform) ----------------------
+    def synthesis_adjoint_rows(self, g: torch.Tensor, n_slices: int, as_real: bool = False, lead=None) -> List[torch.Tensor]:
+        """g [N, length] (gradient w.r.t. the synthesis output) -> per bucket [N, F_b, S, M_b] complex:
+        the transpose of ``backward_rows`` with respect to the real inner product
+        <y, g> = sum y*g, <c, d> = sum Re(c) Re(d) + Im(c) Im(d).  Runs on the analysis kernels
+        with a second plan (no slicing window, dual windows, zero instead of mirrored margins)."""
+        _BACKEND.check(g)
+        if self._adj_tables is None:
+            self._adj_tables = _AdjointTables(self.tables)
+        if g.dtype != torch.float32:
+            g = g.to(torch.float32)
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        N, T = g.shape
+        plan = self._adj_cache.get(self._adj_tables, g.device)
+        with _BACKEND.device_guard(g.device):
+            slab, out = self.alloc_coefficients(N, n_slices, g.device, lead=lead, as_real=as_real)
+            nbytes = plan.scratch_bytes(N, n_slices, False)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+            plan.forward_packed(g.data_ptr(), N, g.stride(0), T, 0, 0, n_slices, slab.data_ptr(),
+                                scratch.data_ptr(), nbytes, _BACKEND.stream(g.device))
+        return out
 
     def backward(self, cseq: Sequence[torch.Tensor], length: int) -> torch.Tensor:
         """slicq.py:198-230: list of [S, N, F_b, M_b] complex -> [N, length].

@@ -85,8 +85,36 @@ class NSGT_SL(nn.Module):
         dev = _module_device(self.nsgt)
         if x.device != dev and x.device.type == "cpu":
             x = x.to(dev)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError(
+                "gradients w.r.t. the analysed waveform are not implemented (the reference never needs them: "
+                "training.py feeds data tensors); gradients through INSGT_SL are (see _InverseFn)")
         x = x.contiguous().view(-1, shape[-1])
         return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True)
+
+
+class _InverseFn(torch.autograd.Function):
+    """Differentiable synthesis: forward = INSGT kernels, backward = their exact adjoint on the
+    analysis kernels (the transform is linear, so no activations are saved).  The reference gets
+    this gradient from torch autograd over nsgt/nsigtf.py + nsgt/unslicing.py, which its README
+    reports as a 5-25x slower epoch; here it costs one analysis pass."""
+
+    @staticmethod
+    def forward(ctx, module, length, *X_list):
+        ctx.module = module
+        ctx.shapes = [tuple(X.shape) for X in X_list]
+        with torch.no_grad():
+            return module._forward_impl(list(X_list), length)
+
+    @staticmethod
+    def backward(ctx, gy):
+        module = ctx.module
+        nsg = module.nsgt.nsgt
+        shp = ctx.shapes[0]
+        lead, S = tuple(shp[:-4]), shp[-3]
+        g = gy.contiguous().view(-1, gy.shape[-1])
+        grads = nsg.synthesis_adjoint_rows(g, S, as_real=True, lead=lead)
+        return (None, None) + tuple(grads)
 
 
 class INSGT_SL(nn.Module):
@@ -101,6 +129,11 @@ class INSGT_SL(nn.Module):
         return self
 
     def forward(self, X_list, length: int) -> Tensor:
+        if torch.is_grad_enabled() and any(X.requires_grad for X in X_list):
+            return _InverseFn.apply(self, length, *X_list)
+        return self._forward_impl(X_list, length)
+
+    def _forward_impl(self, X_list, length: int) -> Tensor:
         dev = _module_device(self.nsgt)
         nsg = self.nsgt.nsgt
         buckets = nsg.tables.buckets
