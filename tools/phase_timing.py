@@ -15,11 +15,11 @@ lib = _cabi.load()
 lib.slicq_debug_set_timing.argtypes = [C.c_void_p]
 names = {0: "start", 1: "load/gather done", 2: "pass A done", 3: "pass B done", 5: "pass C done", 6: "end"}
 def run(label, fn, n_cta):
-    buf = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
     assert lib.slicq_debug_set_timing(C.c_void_p(buf.data_ptr())) == 0
     fn(); torch.cuda.synchronize()
     lib.slicq_debug_set_timing(C.c_void_p(0))
-    t = buf.view(n_cta, 8).cpu()
+    t = buf.view(n_cta, 16).cpu()
     ok = t[:, 6] > 0
     t = t[ok].double()
     print(f"{label}: {int(ok.sum())} CTAs timed; mean cycles per phase:")
@@ -30,6 +30,8 @@ def run(label, fn, n_cta):
         prev = i
     if (t[:, 7] > 0).all():
         print(f"   [thread 0] start -> zero-fill done {(t[:,7]-t[:,0]).mean().item():8.0f}; -> own loads done {(t[:,4]-t[:,7]).mean().item():8.0f}; -> barrier passed {(t[:,1]-t[:,4]).mean().item():8.0f}")
+    print(f"   raw slots: [4]={t[:,4].mean().item():.0f}  [7]-[0]={(t[:,7]-t[:,0]).mean().item():.0f}  [1]-[7]={(t[:,1]-t[:,7]).mean().item():.0f}")
+    print("   slots 8..14 (t0 done-wait, t0 issue, t32 full-wait, t32 process, t32 arrive, t352 full-wait, t352 process):", [round(t[:,i].mean().item()) for i in range(8,15)])
     print(f"   total {((t[:,6]-t[:,0]).mean().item()):10.0f} cycles; kernel span {(t[:,6].max()-t[:,0].min()).item():.0f} cycles")
 S = Cc[0].shape[2]
 run("slice_fft_fwd", lambda: nsg.forward_rows(x), 2 * B * S)

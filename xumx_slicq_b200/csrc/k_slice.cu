@@ -23,16 +23,24 @@
 //            nsgt/unslicing.py:33-69 + nsgt/slicq.py:207-230 (inverse); closed forms in DESIGN.md.
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 // optional per-phase timing (tuning builds only, -DSLICQ_PHASE_TIMING): thread 0 of every CTA stores
 // clock64() at the phase boundaries into a buffer registered with slicq_debug_set_timing()
 // (tools/phase_timing.py).  Compiled out of the product build.
 #if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
 __device__ long long* g_phase_buf = nullptr;
-#define PHASE_MARK(i) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#define PHASE_MARK(i) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#define PHASE_CLOCK() clock64()
+#define PHASE_STORE_T(t, i, v) do { if (threadIdx.x == (t) && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = (v); } while (0)
+#define PHASE_STORE(i, v) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = (v); } while (0)
 extern "C" int slicq_debug_set_timing(long long* buf) { return (int)cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof buf); }
 #else
 #define PHASE_MARK(i) do {} while (0)
+#define PHASE_CLOCK() 0LL
+#define PHASE_STORE(i, v) do {} while (0)
+#define PHASE_STORE_T(t, i, v) do {} while (0)
 extern "C" int slicq_debug_set_timing(long long*) { return -1; }
 #endif
 
@@ -57,9 +65,19 @@ struct Pfa3 {
     static constexpr int SA = (P2 * SB) % 2 == 1 ? P2 * SB + 2 : P2 * SB + 1;  // odd, > P2*SB
     static constexpr int SMEM_ELEMS = P1 * SA;
     static constexpr int I1 = cmodinv(N / P1, P1), I2 = cmodinv(N / P2, P2), I3 = cmodinv(N / P3, P3);
-    static int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
-    static int pos_out(int k) { return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3); }
+    // shared-memory slot of FFT input index n / output index k: a few integer multiplies (constant
+    // divisors) instead of a table lookup, so the permuted phases have no dependent memory access
+    static __host__ SLICQ_DEVFN int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
+    static __host__ SLICQ_DEVFN int pos_out(int k) { return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3); }
 };
+// -DSLICQ_PERM_TABLE (tuning): take the slots from the plan's perm_in / perm_out tables instead
+#ifdef SLICQ_PERM_TABLE
+#define POS_IN(n) ((int)__ldg(p.t.perm_in + (n)))
+#define POS_OUT(k) ((int)__ldg(p.t.perm_out + (k)))
+#else
+#define POS_IN(n) PF::pos_in(n)
+#define POS_OUT(k) PF::pos_out(k)
+#endif
 
 template <class PF, bool INV>
 SLICQ_DEVFN void pfa_passes(float2* Z) {
@@ -125,15 +143,6 @@ SLICQ_DEVFN void pfa_passes(float2* Z) {
     __syncthreads();
 }
 
-// sum of the windowed bin spectra covering one position (fixed bin order -> deterministic)
-SLICQ_DEVFN float2 gather_spectrum(const int4 o, const float2* __restrict__ row) {
-    float2 acc = row[o.x];
-    if (o.y >= 0) { const float2 v = row[o.y]; acc.x += v.x; acc.y += v.y; }
-    if (o.z >= 0) { const float2 v = row[o.z]; acc.x += v.x; acc.y += v.y; }
-    if (o.w >= 0) { const float2 v = row[o.w]; acc.x += v.x; acc.y += v.y; }
-    return acc;
-}
-
 }  // namespace
 
 typedef Pfa3<43, 15, 14> Pfa9030;
@@ -151,12 +160,11 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     PHASE_MARK(0);
     const float* __restrict__ xr = p.x + row * p.x_row_stride;
     const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
-    const unsigned short* __restrict__ pin = p.t.perm_in;
     const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;
     // zero part of the window: no loads
     for (int e = threadIdx.x; e < N - (e_hi - e_lo); e += blockDim.x) {
         const int ee = e < e_lo ? e : e + (e_hi - e_lo);
-        Z[__ldg(pin + ee)] = make_float2(0.f, 0.f);
+        Z[POS_IN(ee)] = make_float2(0.f, 0.f);
     }
     PHASE_MARK(7);
     const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;   // x range touched by the window support
@@ -167,16 +175,15 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
         const float2* __restrict__ x2 = reinterpret_cast<const float2*>(xr + s0);
         for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += U * blockDim.x) {
             float2 v[U], w[U];
-            int pi[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * blockDim.x;
-                if (e < e_hi) { pi[u] = __ldg(pin + e); w[u] = __ldg(tw2 + e); v[u] = __ldg(x2 + e); }
+                if (e < e_hi) { w[u] = __ldg(tw2 + e); v[u] = __ldg(x2 + e); }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * blockDim.x;
-                if (e < e_hi) Z[pi[u]] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
+                if (e < e_hi) Z[POS_IN(e)] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
             }
         }
     } else {
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             float a = 0.f, b = 0.f;
             if (s >= 0 && s < p.T) a = __ldg(xr + s) * w.x;
             if (s + 1 >= 0 && s + 1 < p.T) b = __ldg(xr + s + 1) * w.y;
-            Z[__ldg(pin + e)] = make_float2(a, b);
+            Z[POS_IN(e)] = make_float2(a, b);
         }
     }
     PHASE_MARK(4);
@@ -197,7 +204,6 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     // even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O); mirrored margins for the bins
     // that reach below DC / above Nyquist (Hermitian symmetry of a real slice)
     float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
-    const unsigned short* __restrict__ pout = p.t.perm_out;
     const int pad_l = p.t.pad_l, pad_r = p.t.pad_r;
     const float sc = p.t.spec_scale, se = p.t.ends_scale;
     const float mir = p.t.adjoint ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
             const int kk = kk0 + u * blockDim.x;
-            if (kk <= N / 2) { pk[u] = __ldg(pout + kk); pn[u] = __ldg(pout + N - kk); wk[u] = __ldg(p.t.post_tw + kk); }
+            if (kk <= N / 2) { pk[u] = POS_OUT(kk); pn[u] = POS_OUT(kk == 0 ? 0 : N - kk); wk[u] = __ldg(p.t.post_tw + kk); }
         }
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
@@ -251,49 +257,98 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const int row = rs / p.S, k = rs - row * p.S;
     if ((k & 1) != p.parity) return;
     PHASE_MARK(0);
+    // ---- gather of the windowed bin spectra + Hermitian pre-processing.
+    // Spectrum position f is the sum over the bins j = jlo .. jlo + n (n <= 3) covering it of
+    // T[f + gd[j]], always in the order (T_jlo + T_jlo+1) + (T_jlo+2 + T_jlo+3): deterministic.
+    // Under load a dependent global access costs a full L2/HBM round trip (~1000 cycles), so the phase
+    // is organised in as few round trips as possible:
+    //   1. tables: gd -> shared memory, this thread's NW pair descriptors and its "extra" entry -> registers
+    //   2. the rare third/fourth terms (gx list, < 5 % of the positions) are summed into Z / RN,
+    //      overlapped with the loads of round 0
+    //   3. NW / UG rounds: the first two terms of UG pairs (k, N-k) and their twiddle in flight together
+    int* gd = reinterpret_cast<int*>(Z + ((PF::SMEM_ELEMS + 1) & ~1));
+    float2* RN = reinterpret_cast<float2*>(gd + ((p.t.n_bins + 4 + 3) & ~3));
+    const int tid = threadIdx.x;
+    constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = 3, NR = (NW + UG - 1) / UG;
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
-    const unsigned short* __restrict__ pin = p.t.perm_in;
-    constexpr int UG = 2;
-    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UG * blockDim.x) {
-        int4 ok[UG], on[UG];
-        int pk[UG], pn[UG];
-        float2 wk[UG];
+    for (int j = tid; j < p.t.n_bins + 4; j += NT) gd[j] = j < p.t.n_bins ? __ldg(p.t.gd + j) : 0;   // 4 pad entries
+    unsigned dsc[NR * UG];
+#pragma unroll
+    for (int u = 0; u < NR * UG; ++u) {
+        const int kk = tid + u * NT;
+        dsc[u] = (kk <= N / 2) ? __ldg(p.t.gjp + kk) : 0u;
+    }
+    const int nx = p.t.n_gx;
+    int4 xe = make_int4(-1, 0, -1, 0);
+    if (tid < nx) xe = __ldg(p.t.gx + tid);
+    __syncthreads();
+    float2 a[UG][4], w[UG];
+    auto load_round = [&](int r) {
 #pragma unroll
         for (int u = 0; u < UG; ++u) {
-            const int kk = kk0 + u * blockDim.x;
-            if (kk <= N / 2) {
-                ok[u] = __ldg(p.t.goff + kk); on[u] = __ldg(p.t.goff + N - kk);
-                pk[u] = __ldg(pin + kk); pn[u] = __ldg(pin + (kk == 0 ? 0 : N - kk)); wk[u] = __ldg(p.t.post_tw + kk);
-            }
-        }
-        float2 rk[UG], rn[UG];
-#pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int kk = kk0 + u * blockDim.x;
-            if (kk <= N / 2) { rk[u] = gather_spectrum(ok[u], Trow); rn[u] = gather_spectrum(on[u], Trow); }
-        }
-#pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int kk = kk0 + u * blockDim.x;
+            const int kk = tid + (r * UG + u) * NT;
             if (kk > N / 2) continue;
+            const unsigned d = dsc[r * UG + u];
+            const int* dk = gd + (d & 0x3fffu);
+            const int* dn = gd + ((d >> 16) & 0x3fffu);
+            a[u][0] = __ldg(Trow + kk + dk[0]);
+            if (((d >> 14) & 3u) >= 1u) a[u][1] = __ldg(Trow + kk + dk[1]);
+            a[u][2] = __ldg(Trow + (N - kk) + dn[0]);
+            if ((d >> 30) >= 1u) a[u][3] = __ldg(Trow + (N - kk) + dn[1]);
+            w[u] = __ldg(p.t.post_tw + kk);
+        }
+    };
+    auto consume_round = [&](int r) {
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int kk = tid + (r * UG + u) * NT;
+            if (kk > N / 2) continue;
+            const unsigned d = dsc[r * UG + u];
+            const unsigned nk = (d >> 14) & 3u, nn = d >> 30;
+            const int pk = POS_IN(kk);
+            const int pn = POS_IN(kk == 0 ? 0 : N - kk);
+            float2 rk = a[u][0], rn = a[u][2];
+            if (nk >= 1u) { rk.x += a[u][1].x; rk.y += a[u][1].y; }
+            if (nn >= 1u) { rn.x += a[u][3].x; rn.y += a[u][3].y; }
+            if (nk >= 2u) { const float2 e = Z[pk]; rk.x += e.x; rk.y += e.y; }
+            if (nn >= 2u) { const float2 e = (kk == 0) ? *RN : Z[pn]; rn.x += e.x; rn.y += e.y; }
             if (kk == 0) {
                 // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
-                Z[pk[u]] = make_float2(rk[u].x + rn[u].x, rk[u].x - rn[u].x);
+                Z[pk] = make_float2(rk.x + rn.x, rk.x - rn.x);
             } else {
-                const float2 E = make_float2(rk[u].x + rn[u].x, rk[u].y - rn[u].y);   // rk + conj(rn)
-                const float2 O = make_float2(rk[u].x - rn[u].x, rk[u].y + rn[u].y);   // rk - conj(rn)
-                const float2 t = cmul_conj(O, wk[u]);                                 // conj(w^k) O
-                Z[pk[u]] = make_float2(E.x - t.y, E.y + t.x);       // E + i t
-                Z[pn[u]] = make_float2(E.x + t.y, t.x - E.y);       // conj(E - i t)
+                const float2 E = make_float2(rk.x + rn.x, rk.y - rn.y);   // rk + conj(rn)
+                const float2 O = make_float2(rk.x - rn.x, rk.y + rn.y);   // rk - conj(rn)
+                const float2 t = cmul_conj(O, w[u]);                      // conj(w^k) O
+                Z[pk] = make_float2(E.x - t.y, E.y + t.x);       // E + i t
+                Z[pn] = make_float2(E.x + t.y, t.x - E.y);       // conj(E - i t)
             }
         }
+    };
+    // extras of this thread (entry tid of gx; lists longer than the CTA are finished below)
+    float2 x2 = make_float2(0.f, 0.f), x3 = make_float2(0.f, 0.f);
+    if (xe.x >= 0) { x2 = __ldg(Trow + xe.y); if (xe.z >= 0) x3 = __ldg(Trow + xe.z); }
+    load_round(0);
+    if (xe.x >= 0) {
+        const float2 e = make_float2(x2.x + x3.x, x2.y + x3.y);
+        if (xe.x < N) Z[POS_IN(xe.x)] = e; else *RN = e;
+    }
+    for (int i = tid + NT; i < nx; i += NT) {
+        const int4 q = __ldg(p.t.gx + i);
+        float2 e = __ldg(Trow + q.y);
+        if (q.z >= 0) { const float2 v = __ldg(Trow + q.z); e.x += v.x; e.y += v.y; }
+        if (q.x < N) Z[POS_IN(q.x)] = e; else *RN = e;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        consume_round(r);
+        if (r + 1 < NR) load_round(r + 1);
     }
     __syncthreads();
     PHASE_MARK(1);
     pfa_passes<PF, true>(Z);
     PHASE_MARK(5);
     const float scale = 1.0f / (float)(2 * N);
-    const unsigned short* __restrict__ pout = p.t.perm_out;
     // slice sample p = 2n, 2n+1 goes to y index tb + p;  first half (n < N/2) = hop k-1, second = hop k
     const long long tb = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;
     float* __restrict__ yr = p.x + row * p.x_row_stride;
@@ -303,37 +358,22 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const bool first_to_halo = (k == 0);      // hop -1: other shard (halo) or before the signal (dropped)
     float* __restrict__ halo = (p.halo_out != nullptr && p.k0 > 0) ? p.halo_out + (long long)row * p.t.hop : nullptr;
     const bool vec = ((reinterpret_cast<uintptr_t>(yr + tb) & 7) == 0) && tb >= 0 && tb + 2 * N <= p.T && !first_to_halo;
-    constexpr int UO = 4;
-    for (int n0 = threadIdx.x; n0 < N; n0 += UO * blockDim.x) {
-        int po[UO];
-        float2 old[UO];
-#pragma unroll
-        for (int u = 0; u < UO; ++u) {
-            const int n = n0 + u * blockDim.x;
-            if (n < N) {
-                po[u] = __ldg(pout + n);
-                if (vec && (accumulate && (n < N / 2 || !second_store)))
-                    old[u] = *reinterpret_cast<const float2*>(yr + tb + 2 * n);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UO; ++u) {
-            const int n = n0 + u * blockDim.x;
-            if (n >= N) continue;
-            const float2 z0 = Z[po[u]];
-            float2 z = make_float2(z0.x * scale, z0.y * scale);
-            const bool first = n < N / 2;
-            const bool add = accumulate && (first || !second_store);
-            if (vec) {
-                if (add) { z.x += old[u].x; z.y += old[u].y; }
-                *reinterpret_cast<float2*>(yr + tb + 2 * n) = z;
-            } else if (first && first_to_halo) {
-                if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
-            } else {
-                const long long t = tb + 2 * n;
-                if (t >= 0 && t < p.T) yr[t] = add ? yr[t] + z.x : z.x;
-                if (t + 1 >= 0 && t + 1 < p.T) yr[t + 1] = add ? yr[t + 1] + z.y : z.y;
-            }
+    // The odd slices add into hops an even slice has stored (previous launch): reductions
+    // (red.global.add, no return value) instead of load + add + store, so that this phase has no
+    // global round trip.  y = even + odd either way: bitwise the same two-term sum.
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float2 z0 = Z[POS_OUT(n)];
+        const float2 z = make_float2(z0.x * scale, z0.y * scale);
+        const bool first = n < N / 2;
+        const bool add = accumulate && (first || !second_store);
+        if (vec) {
+            if (add) slicq_red_add2(yr + tb + 2 * n, z); else *reinterpret_cast<float2*>(yr + tb + 2 * n) = z;
+        } else if (first && first_to_halo) {
+            if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
+        } else {
+            const long long t = tb + 2 * n;
+            if (t >= 0 && t < p.T) { if (add) slicq_red_add(yr + t, z.x); else yr[t] = z.x; }
+            if (t + 1 >= 0 && t + 1 < p.T) { if (add) slicq_red_add(yr + t + 1, z.y); else yr[t + 1] = z.y; }
         }
     }
     PHASE_MARK(6);
@@ -343,6 +383,14 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
 extern "C" int slicq_slice_smem_bytes(int L) {
     if (L == 2 * Pfa9030::N) return (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     return -1;
+}
+
+// dynamic shared memory of slice_fft_inv_kernel: Z, per-bin gather offsets (+ 4 pad entries), Nyquist value
+static int slice_inv_smem_bytes(const SlicqDeviceTables& t) {
+    size_t b = (size_t)((Pfa9030::SMEM_ELEMS + 1) & ~1) * sizeof(float2);
+    b += (size_t)((t.n_bins + 4 + 3) & ~3) * sizeof(int);
+    b += 2 * sizeof(float2);
+    return (int)b;
 }
 
 // fills perm_in[N] and perm_out[N+1] for slice length L (host)
@@ -369,9 +417,9 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
     if (p->t.L != 2 * Pfa9030::N) return -2;
-    const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
+    const int smem = slice_inv_smem_bytes(p->t);
     static int attr_done = 0;
-    if (!attr_done) { SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem); attr_done = 1; }
+    if (attr_done < smem) { SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem); attr_done = smem; }
     SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
     return (int)cudaGetLastError();
 }

@@ -301,19 +301,37 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
             const double a = -2.0 * M_PI * (double)j / (double)b.M;
             tw[b.tw_off + j] = make_float2((float)cos(a), (float)sin(a));
         }
-    std::vector<int4> goff(p->N2 + 1);
+    // synthesis gather tables (slice_fft_inv_kernel): the bins covering a position are consecutive,
+    // bin j contributes T[f + gd[j]]; positions are scheduled by the chunk of T their last term lies in
+    std::vector<int> gd(J);
+    for (int j = 0; j < J; ++j) gd[j] = p->bin_coff[j] - p->bin_pos[j] + p->bin_M[j] / 2;
+    std::vector<unsigned> gj(p->N2 + 1);
+    std::vector<int4> gx;
+    if (J >= (1 << 14)) { delete p; return fail(SLICQ_E_UNSUPPORTED, "too many bins for the gather descriptors"); }
     for (int f = 0; f <= p->N2; ++f) {
-        int o[4] = {-1, -1, -1, -1}, n = 0;
+        int jlo = -1, jhi = -1, n = 0;
         for (int j = 0; j < J; ++j) {
             const int d = f - p->bin_pos[j], h = p->bin_M[j] / 2;
             if (d >= -h && d < h) {
-                if (n == 4) { delete p; return fail(SLICQ_E_UNSUPPORTED, "more than 4 bins overlap at one spectrum position"); }
-                o[n++] = p->bin_coff[j] + d + h;   // centred order
+                if (jlo < 0) jlo = j;
+                jhi = j;
+                ++n;
             }
         }
         if (n == 0) { delete p; return fail(SLICQ_E_UNSUPPORTED, "spectrum position not covered by any bin"); }
-        goff[f].x = o[0]; goff[f].y = o[1]; goff[f].z = o[2]; goff[f].w = o[3];
+        if (n > 4) { delete p; return fail(SLICQ_E_UNSUPPORTED, "more than 4 bins overlap at one spectrum position"); }
+        if (jhi - jlo + 1 != n) { delete p; return fail(SLICQ_E_UNSUPPORTED, "bins covering a spectrum position are not consecutive"); }
+        gj[f] = (unsigned)(jlo | ((n - 1) << 14));
+        if (n >= 3) {
+            int4 e;
+            e.x = f; e.y = f + gd[jlo + 2]; e.z = (n == 4) ? f + gd[jlo + 3] : -1; e.w = 0;
+            gx.push_back(e);
+        }
     }
+    std::vector<unsigned> gjp(p->N2 / 2 + 1);
+    for (int k = 0; k <= p->N2 / 2; ++k) gjp[k] = gj[k] | (gj[p->N2 - k] << 16);
+    const int n_gx = (int)gx.size();
+    if (gx.empty()) gx.push_back(int4{-1, 0, -1, 0});
     std::vector<unsigned short> perm_in(p->N2), perm_out(p->N2 + 1);
     if (slicq_slice_perm(L, perm_in.data(), perm_out.data()) != 0) {
         delete p;
@@ -336,7 +354,10 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(p->bin_coff, &d.bin_coff, p->owned);
     rc |= upload(post, &d.post_tw, p->owned);
     rc |= upload(tw, &d.tw, p->owned);
-    rc |= upload(goff, &d.goff, p->owned);
+    rc |= upload(gjp, &d.gjp, p->owned);
+    rc |= upload(gd, &d.gd, p->owned);
+    rc |= upload(gx, &d.gx, p->owned);
+    d.n_gx = n_gx;
     rc |= upload(perm_in, &d.perm_in, p->owned);
     rc |= upload(perm_out, &d.perm_out, p->owned);
     if (rc) {
