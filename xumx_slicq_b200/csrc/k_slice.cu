@@ -44,6 +44,9 @@ extern "C" int slicq_debug_set_timing(long long* buf) { return (int)cudaMemcpyTo
 extern "C" int slicq_debug_set_timing(long long*) { return -1; }
 #endif
 
+#ifndef SLICQ_GATHER_UG
+#define SLICQ_GATHER_UG 3   // spectrum pairs per thread and round of the synthesis gather
+#endif
 #ifndef SLICQ_SLICE_THREADS
 #define SLICQ_SLICE_THREADS 384
 #endif
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     int* gd = reinterpret_cast<int*>(Z + ((PF::SMEM_ELEMS + 1) & ~1));
     float2* RN = reinterpret_cast<float2*>(gd + ((p.t.n_bins + 4 + 3) & ~3));
     const int tid = threadIdx.x;
-    constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = 3, NR = (NW + UG - 1) / UG;
+    constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = SLICQ_GATHER_UG, NR = (NW + UG - 1) / UG;
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
     for (int j = tid; j < p.t.n_bins + 4; j += NT) gd[j] = j < p.t.n_bins ? __ldg(p.t.gd + j) : 0;   // 4 pad entries
     unsigned dsc[NR * UG];

@@ -135,6 +135,7 @@ template <class T> int upload(const std::vector<T>& h, const T** d, std::vector<
 
 }  // namespace
 
+#define SLICQ_MAX_WAYS 8
 struct slicq_plan {
     int L, N2, hop, J, sum_M;
     std::vector<int> bin_M, bin_pos, bin_coff;
@@ -152,8 +153,9 @@ struct slicq_plan {
     // joined back into the caller's stream): the memory-latency-bound and the issue-bound kernels of
     // the two halves overlap on the SMs.  Rows are independent, so the results do not change.
     long long split_units;          // split when the call has at least this many units (0 = never)
-    mutable cudaStream_t side[2];
-    mutable cudaEvent_t ev_fork, ev_join[2];
+    int split_ways;                 // row groups / internal streams of a split call (2 .. SLICQ_MAX_WAYS)
+    mutable cudaStream_t side[SLICQ_MAX_WAYS];
+    mutable cudaEvent_t ev_fork, ev_join[SLICQ_MAX_WAYS];
     mutable bool side_ready;
 };
 
@@ -182,8 +184,8 @@ extern "C" int slicq_profile_read(double* ms, int64_t* launches) {
 extern "C" void slicq_plan_destroy(slicq_plan* p) {
     if (!p) return;
     if (p->side_ready) {
-        cudaStreamDestroy(p->side[0]); cudaStreamDestroy(p->side[1]);
-        cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join[0]); cudaEventDestroy(p->ev_join[1]);
+        for (int h = 0; h < SLICQ_MAX_WAYS; ++h) { cudaStreamDestroy(p->side[h]); cudaEventDestroy(p->ev_join[h]); }
+        cudaEventDestroy(p->ev_fork);
     }
     for (void* q : p->owned) cudaFree(q);
     delete p;
@@ -261,7 +263,8 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
             return fail(SLICQ_E_UNSUPPORTED, "bucket has too many bins for one CTA");
         }
         b.gt = gt;
-        const int sm = b.n_bins * gt * b.smem_per_fft + 4096;   // + SLICQ_SLOT_BYTES
+        // + SLICQ_SLOT_BYTES; single-thread transforms keep the bucket's windows behind the stage
+        const int sm = b.n_bins * gt * b.smem_per_fft + 4096 + (f->kind == 1 ? b.n_bins * b.M * 4 + 16 : 0);
         if (sm > p->bins_smem) p->bins_smem = sm;
         // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
         b.cost = (double)b.n_bins * b.M * (log2((double)b.M) + (f->kind == 3 ? 0.12 * f->A : 0.0) + 4.0);
@@ -374,6 +377,10 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     if (p->target_jobs < 1) p->target_jobs = 1;
     const char* envs = getenv("SLICQ_SPLIT_UNITS");
     p->split_units = envs ? atoll(envs) : 1184;
+    const char* envw = getenv("SLICQ_SPLIT_WAYS");
+    p->split_ways = envw ? atoi(envw) : 2;
+    if (p->split_ways < 2) p->split_ways = 2;
+    if (p->split_ways > SLICQ_MAX_WAYS) p->split_ways = SLICQ_MAX_WAYS;
     p->side_ready = false;
     const char* envb = getenv("SLICQ_ONLY_BUCKET");
     p->only_bucket = envb ? atoi(envb) : -1;
@@ -417,6 +424,9 @@ namespace {
 bool use_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices) {
     return p->split_units > 0 && n_rows >= 2 && n_rows * n_slices >= p->split_units;
 }
+// rows are dealt to `ways` groups of (almost) equal size; group h = rows [part_row0(h), part_row0(h + 1))
+int split_ways(const slicq_plan* p, int64_t n_rows) { return (int)(n_rows < p->split_ways ? n_rows : p->split_ways); }
+int64_t part_row0(int64_t n_rows, int ways, int h) { return n_rows * h / ways; }
 size_t half_scratch(const slicq_plan* p, int64_t rows, int64_t n_slices, int inverse) {
     long long units = rows * n_slices;
     const long long c = chunk_units(p, inverse);
@@ -425,10 +435,10 @@ size_t half_scratch(const slicq_plan* p, int64_t rows, int64_t n_slices, int inv
 }
 int ensure_side_streams(const slicq_plan* p) {
     if (p->side_ready) return 0;
-    if (cudaStreamCreateWithFlags(&p->side[0], cudaStreamNonBlocking) || cudaStreamCreateWithFlags(&p->side[1], cudaStreamNonBlocking) ||
-        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) || cudaEventCreateWithFlags(&p->ev_join[0], cudaEventDisableTiming) ||
-        cudaEventCreateWithFlags(&p->ev_join[1], cudaEventDisableTiming))
-        return -1;
+    if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming)) return -1;
+    for (int h = 0; h < SLICQ_MAX_WAYS; ++h)
+        if (cudaStreamCreateWithFlags(&p->side[h], cudaStreamNonBlocking) || cudaEventCreateWithFlags(&p->ev_join[h], cudaEventDisableTiming))
+            return -1;
     p->side_ready = true;
     return 0;
 }
@@ -436,8 +446,13 @@ int ensure_side_streams(const slicq_plan* p) {
 
 extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse) {
     if (!p || n_rows <= 0 || n_slices <= 0) return 0;
-    if (use_split(p, n_rows, n_slices))
-        return half_scratch(p, n_rows / 2, n_slices, inverse) + half_scratch(p, n_rows - n_rows / 2, n_slices, inverse) + 256;
+    if (use_split(p, n_rows, n_slices)) {
+        const int ways = split_ways(p, n_rows);
+        size_t total = 256;
+        for (int h = 0; h < ways; ++h)
+            total += half_scratch(p, part_row0(n_rows, ways, h + 1) - part_row0(n_rows, ways, h), n_slices, inverse);
+        return total;
+    }
     return half_scratch(p, n_rows, n_slices, inverse) + 256;
 }
 
@@ -482,17 +497,19 @@ int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const sli
                 int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
                 int64_t t0, float* halo_out, void* scratch, cudaStream_t s);
 
-// run `fn(half, row0, rows, scratch, stream)` for the two row halves on the plan's side streams
+// run `fn(row0, rows, scratch, stream)` for the row groups on the plan's side streams
 template <class F>
 int run_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse, void* scratch, cudaStream_t s, F fn) {
     if (ensure_side_streams(p)) return fail(SLICQ_E_CUDA, "cannot create internal streams");
-    const int64_t ra = n_rows / 2, rb = n_rows - ra;
+    const int ways = split_ways(p, n_rows);
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
     cudaEventRecord(p->ev_fork, s);
     int rc = 0;
-    for (int h = 0; h < 2 && rc == 0; ++h) {
+    for (int h = 0; h < ways && rc == 0; ++h) {
+        const int64_t r0 = part_row0(n_rows, ways, h), rows = part_row0(n_rows, ways, h + 1) - r0;
         cudaStreamWaitEvent(p->side[h], p->ev_fork, 0);
-        rc = fn(h == 0 ? 0 : ra, h == 0 ? ra : rb, base + (h == 0 ? 0 : half_scratch(p, ra, n_slices, inverse)), p->side[h]);
+        rc = fn(r0, rows, base, p->side[h]);
+        base += half_scratch(p, rows, n_slices, inverse);
         cudaEventRecord(p->ev_join[h], p->side[h]);
         cudaStreamWaitEvent(s, p->ev_join[h], 0);
     }

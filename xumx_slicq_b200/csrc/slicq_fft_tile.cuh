@@ -74,18 +74,30 @@ SLICQ_DEVFN void ana_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
     const int tid = threadIdx.x;
     const int gs = tid / j.F, f = tid - gs * j.F;
     const bool act = gs < j.gt;
-    float w[M];
+    // window of the thread's bin: registers for the short transforms, shared memory (behind the
+    // stage) for M > 24, where the codelet needs the registers itself
+    constexpr bool WREG = M <= 24;
+    float w[WREG ? M : 1];
     int hoff = 0;
     if (act) {
         const int bin = j.first_bin + f;
         const int coff = __ldg(p.t.bin_coff + bin);
         hoff = p.t.pad_l + __ldg(p.t.bin_pos + bin) - M / 2;
+        if (WREG) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) w[m] = __ldg(p.t.wf + coff + m);
+            for (int m = 0; m < (WREG ? M : 1); ++m) w[m] = __ldg(p.t.wf + coff + m);
+        }
     }
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
     float2* stage = sm + (gs * j.F + f) * PITCH;
+    const float* wsm = reinterpret_cast<const float*>(sm + j.gt * j.F * PITCH) + f * M;
+    if (!WREG) {
+        float* wd = reinterpret_cast<float*>(sm + j.gt * j.F * PITCH);
+        const int coff0 = __ldg(p.t.bin_coff + j.first_bin);
+        for (int t = tid; t < j.F * M; t += blockDim.x) wd[t] = __ldg(p.t.wf + coff0 + t);
+        __syncthreads();
+    }
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int g = base + gs;
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
@@ -96,8 +108,9 @@ SLICQ_DEVFN void ana_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
 #pragma unroll
             for (int m = 0; m < M; m += 2) {
                 const float4 x = h[m >> 1];
-                v[m] = make_float2(x.x * w[m], x.y * w[m]);
-                v[m + 1] = make_float2(x.z * w[m + 1], x.w * w[m + 1]);
+                const float w0 = WREG ? w[WREG ? m : 0] : wsm[m], w1 = WREG ? w[WREG ? m + 1 : 0] : wsm[m + 1];
+                v[m] = make_float2(x.x * w0, x.y * w0);
+                v[m + 1] = make_float2(x.z * w1, x.w * w1);
             }
             dft<M, true>(v);
 #pragma unroll
@@ -112,27 +125,38 @@ SLICQ_DEVFN void ana_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
     }
 }
 
+// synthesis: coefficients come in through shared memory (coalesced 16-byte loads), every thread
+// transforms one row in place, and the windowed spectra of a unit -- one contiguous block
+// [coff_first, coff_first + F*M) of the packed row T -- leave through shared memory again.
 template <int M>
 SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float2* sm) {
     constexpr int PITCH = M + 1;
     const int tid = threadIdx.x;
     const int gs = tid / j.F, f = tid - gs * j.F;
     const bool act = gs < j.gt;
-    float w[M];
-    int coff = 0;
-    if (act) {
-        coff = __ldg(p.t.bin_coff + j.first_bin + f);
-#pragma unroll
-        for (int m = 0; m < M; ++m) w[m] = __ldg(p.t.wi + coff + m);
-    }
+    const int coff0 = __ldg(p.t.bin_coff + j.first_bin);
+    const int FM = j.F * M;
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
-    const float2* stage = sm + (gs * j.F + f) * PITCH;
+    float2* stage = sm + (gs * j.F + f) * PITCH;
+    // the bucket's dual windows (contiguous in wi, like the bins in T) live behind the stage and are
+    // applied on the way out: no per-thread window registers next to the M-point codelet
+    float* wsm = reinterpret_cast<float*>(sm + j.gt * j.F * PITCH);
+    for (int t = tid; t < FM; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff0 + t);
+    const bool vec = b.mptr == nullptr && ((reinterpret_cast<uintptr_t>(b.ptr) & 15) == 0) &&
+                     (((b.s_row | b.s_bin | b.s_slice) & 1) == 0);
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
         __syncthreads();
-        if (b.mptr == nullptr) {
+        if (vec) {
+            for (int t = tid; t < ng * j.F * (M / 2); t += blockDim.x) {
+                const int slot = t / (M / 2), n = 2 * (t - slot * (M / 2));
+                const float4 v = *reinterpret_cast<const float4*>(b.ptr + so[slot] + n);
+                sm[slot * PITCH + n] = make_float2(v.x, v.y);
+                sm[slot * PITCH + n + 1] = make_float2(v.z, v.w);
+            }
+        } else if (b.mptr == nullptr) {
             for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
                 const int slot = t / M, n = t - slot * M;
                 sm[slot * PITCH + n] = b.ptr[so[slot] + n];
@@ -144,18 +168,24 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
             }
         }
         __syncthreads();
-        const int g = base + gs;
-        if (act && g < j.u1) {
+        if (act && base + gs < j.u1) {
             float2 v[M];
 #pragma unroll
             for (int n = 0; n < M; ++n) v[n] = cneg_if(stage[n], n & 1);
             dft<M, false>(v);
-            float4* o = reinterpret_cast<float4*>(p.spec + (long long)g * p.spec_stride + coff);
 #pragma unroll
-            for (int m = 0; m < M; m += 2)
-                o[m >> 1] = make_float4(v[m].x * w[m], v[m].y * w[m], v[m + 1].x * w[m + 1], v[m + 1].y * w[m + 1]);
+            for (int m = 0; m < M; ++m) stage[m] = v[m];
         }
         __syncthreads();
+        // rows of T are 16-byte aligned and coff / M are even: two coefficients per store
+        for (int t = tid; t < ng * (FM / 2); t += blockDim.x) {
+            const int g = t / (FM / 2), e = 2 * (t - g * (FM / 2));
+            const int fb = e / M, n = e - fb * M;
+            const float2* src = sm + (g * j.F + fb) * PITCH + n;
+            const float w0 = wsm[e], w1 = wsm[e + 1];
+            *reinterpret_cast<float4*>(p.spec + (long long)(base + g) * p.spec_stride + coff0 + e) =
+                make_float4(src[0].x * w0, src[0].y * w0, src[1].x * w1, src[1].y * w1);
+        }
     }
 }
 
