@@ -47,6 +47,9 @@ extern "C" int slicq_debug_set_timing(long long*) { return -1; }
 #ifndef SLICQ_GATHER_UG
 #define SLICQ_GATHER_UG 3   // spectrum pairs per thread and round of the synthesis gather
 #endif
+#ifndef SLICQ_FWD_LOADS
+#define SLICQ_FWD_LOADS 6
+#endif
 #ifndef SLICQ_SLICE_THREADS
 #define SLICQ_SLICE_THREADS 384
 #endif
@@ -72,15 +75,28 @@ struct Pfa3 {
     // divisors) instead of a table lookup, so the permuted phases have no dependent memory access
     static __host__ SLICQ_DEVFN int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
     static __host__ SLICQ_DEVFN int pos_out(int k) { return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3); }
+    // Residue walker: the load / store phases visit indices tid + i * blockDim, so they keep the three
+    // residues of the index and advance them by a constant (one add and one conditional subtract
+    // each) instead of dividing three times per element.
+    struct Walk { int a, b, c; };
+    static SLICQ_DEVFN Walk walk_in(int n) { Walk w; w.a = n % P1; w.b = n % P2; w.c = n % P3; return w; }
+    static SLICQ_DEVFN Walk walk_out(int k) { Walk w; w.a = (k * I1) % P1; w.b = (k * I2) % P2; w.c = (k * I3) % P3; return w; }
+    static SLICQ_DEVFN Walk add_res(Walk w, int da, int db, int dc) {   // da < P1, db < P2, dc < P3
+        w.a += da; if (w.a >= P1) w.a -= P1;
+        w.b += db; if (w.b >= P2) w.b -= P2;
+        w.c += dc; if (w.c >= P3) w.c -= P3;
+        return w;
+    }
+    static SLICQ_DEVFN Walk step_in(Walk w, int d) { return add_res(w, d % P1, d % P2, d % P3); }     // index + d, d >= 0
+    static SLICQ_DEVFN Walk step_out(Walk w, int d) { return add_res(w, ((d % P1) * I1) % P1, ((d % P2) * I2) % P2, ((d % P3) * I3) % P3); }
+    static SLICQ_DEVFN Walk neg(Walk w) {   // residues of N - index
+        w.a = w.a ? P1 - w.a : 0; w.b = w.b ? P2 - w.b : 0; w.c = w.c ? P3 - w.c : 0;
+        return w;
+    }
+    static SLICQ_DEVFN int slot(Walk w) { return w.a * SA + w.b * SB + w.c; }
 };
-// -DSLICQ_PERM_TABLE (tuning): take the slots from the plan's perm_in / perm_out tables instead
-#ifdef SLICQ_PERM_TABLE
-#define POS_IN(n) ((int)__ldg(p.t.perm_in + (n)))
-#define POS_OUT(k) ((int)__ldg(p.t.perm_out + (k)))
-#else
 #define POS_IN(n) PF::pos_in(n)
 #define POS_OUT(k) PF::pos_out(k)
-#endif
 
 template <class PF, bool INV>
 SLICQ_DEVFN void pfa_passes(float2* Z) {
@@ -165,38 +181,44 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
     const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;
     // zero part of the window: no loads
-    for (int e = threadIdx.x; e < N - (e_hi - e_lo); e += blockDim.x) {
-        const int ee = e < e_lo ? e : e + (e_hi - e_lo);
-        Z[POS_IN(ee)] = make_float2(0.f, 0.f);
+    constexpr int NT = SLICQ_SLICE_THREADS;
+    {
+        typename PF::Walk wz = PF::walk_in(threadIdx.x);
+        for (int e = threadIdx.x; e < e_lo; e += NT) { Z[PF::slot(wz)] = make_float2(0.f, 0.f); wz = PF::step_in(wz, NT); }
+        wz = PF::walk_in(e_hi + threadIdx.x);
+        for (int e = e_hi + threadIdx.x; e < N; e += NT) { Z[PF::slot(wz)] = make_float2(0.f, 0.f); wz = PF::step_in(wz, NT); }
     }
     PHASE_MARK(7);
     const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;   // x range touched by the window support
     const bool interior = sa >= 0 && sb <= p.T;
     const bool vec = ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
-    constexpr int U = 4;   // loads in flight per thread
+    constexpr int U = SLICQ_FWD_LOADS;   // sample pairs in flight per thread: the phase costs one memory round trip per U * NT pairs
+    typename PF::Walk wl = PF::walk_in(e_lo + threadIdx.x);
     if (interior && vec) {
         const float2* __restrict__ x2 = reinterpret_cast<const float2*>(xr + s0);
-        for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += U * blockDim.x) {
+        for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += U * NT) {
             float2 v[U], w[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * blockDim.x;
+                const int e = e0 + u * NT;
                 if (e < e_hi) { w[u] = __ldg(tw2 + e); v[u] = __ldg(x2 + e); }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * blockDim.x;
-                if (e < e_hi) Z[POS_IN(e)] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
+                const int e = e0 + u * NT;
+                if (e < e_hi) Z[PF::slot(PF::step_in(wl, u * NT))] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
             }
+            wl = PF::step_in(wl, U * NT);
         }
     } else {
-        for (int e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+        for (int e = e_lo + threadIdx.x; e < e_hi; e += NT) {
             const long long s = s0 + 2 * e;
             const float2 w = __ldg(tw2 + e);
             float a = 0.f, b = 0.f;
             if (s >= 0 && s < p.T) a = __ldg(xr + s) * w.x;
             if (s + 1 >= 0 && s + 1 < p.T) b = __ldg(xr + s + 1) * w.y;
-            Z[POS_IN(e)] = make_float2(a, b);
+            Z[PF::slot(wl)] = make_float2(a, b);
+            wl = PF::step_in(wl, NT);
         }
     }
     PHASE_MARK(4);
@@ -211,17 +233,23 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     const float sc = p.t.spec_scale, se = p.t.ends_scale;
     const float mir = p.t.adjoint ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
     constexpr int UP = 4;
-    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UP * blockDim.x) {
+    typename PF::Walk wp = PF::walk_out(threadIdx.x);
+    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UP * NT) {
         int pk[UP], pn[UP];
         float2 wk[UP];
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
-            const int kk = kk0 + u * blockDim.x;
-            if (kk <= N / 2) { pk[u] = POS_OUT(kk); pn[u] = POS_OUT(kk == 0 ? 0 : N - kk); wk[u] = __ldg(p.t.post_tw + kk); }
+            const int kk = kk0 + u * NT;
+            if (kk <= N / 2) {
+                const typename PF::Walk wq = PF::step_out(wp, u * NT);
+                pk[u] = PF::slot(wq); pn[u] = PF::slot(PF::neg(wq));    // slots of output kk and N - kk (kk = 0: both slot 0)
+                wk[u] = __ldg(p.t.post_tw + kk);
+            }
         }
+        wp = PF::step_out(wp, UP * NT);
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
-            const int kk = kk0 + u * blockDim.x;
+            const int kk = kk0 + u * NT;
             if (kk > N / 2) continue;
             const float2 zk = Z[pk[u]];
             if (kk == 0) {
@@ -273,7 +301,11 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     float2* RN = reinterpret_cast<float2*>(gd + ((p.t.n_bins + 4 + 3) & ~3));
     const int tid = threadIdx.x;
     constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = SLICQ_GATHER_UG, NR = (NW + UG - 1) / UG;
+    #ifdef SLICQ_DEBUG_TWRAP
+    const float2* __restrict__ Trow = p.spec + (long long)(rsl % SLICQ_DEBUG_TWRAP) * p.spec_stride;   // tuning experiment, see slicq_fft_tile.cuh
+#else
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
+#endif
     for (int j = tid; j < p.t.n_bins + 4; j += NT) gd[j] = j < p.t.n_bins ? __ldg(p.t.gd + j) : 0;   // 4 pad entries
     unsigned dsc[NR * UG];
 #pragma unroll
@@ -286,6 +318,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     if (tid < nx) xe = __ldg(p.t.gx + tid);
     __syncthreads();
     float2 a[UG][4], w[UG];
+    const typename PF::Walk wk0 = PF::walk_in(tid);
     auto load_round = [&](int r) {
 #pragma unroll
         for (int u = 0; u < UG; ++u) {
@@ -308,8 +341,8 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             if (kk > N / 2) continue;
             const unsigned d = dsc[r * UG + u];
             const unsigned nk = (d >> 14) & 3u, nn = d >> 30;
-            const int pk = POS_IN(kk);
-            const int pn = POS_IN(kk == 0 ? 0 : N - kk);
+            const typename PF::Walk wkk = PF::step_in(wk0, (r * UG + u) * NT);
+            const int pk = PF::slot(wkk), pn = PF::slot(PF::neg(wkk));      // slots of kk and N - kk (kk = 0: both slot 0)
             float2 rk = a[u][0], rn = a[u][2];
             if (nk >= 1u) { rk.x += a[u][1].x; rk.y += a[u][1].y; }
             if (nn >= 1u) { rn.x += a[u][3].x; rn.y += a[u][3].y; }
@@ -364,19 +397,30 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     // The odd slices add into hops an even slice has stored (previous launch): reductions
     // (red.global.add, no return value) instead of load + add + store, so that this phase has no
     // global round trip.  y = even + odd either way: bitwise the same two-term sum.
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const float2 z0 = Z[POS_OUT(n)];
-        const float2 z = make_float2(z0.x * scale, z0.y * scale);
-        const bool first = n < N / 2;
-        const bool add = accumulate && (first || !second_store);
-        if (vec) {
-            if (add) slicq_red_add2(yr + tb + 2 * n, z); else *reinterpret_cast<float2*>(yr + tb + 2 * n) = z;
-        } else if (first && first_to_halo) {
-            if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
-        } else {
-            const long long t = tb + 2 * n;
-            if (t >= 0 && t < p.T) { if (add) slicq_red_add(yr + t, z.x); else yr[t] = z.x; }
-            if (t + 1 >= 0 && t + 1 < p.T) { if (add) slicq_red_add(yr + t + 1, z.y); else yr[t + 1] = z.y; }
+    typename PF::Walk wo = PF::walk_out(threadIdx.x);
+    if (vec) {
+        const bool add1 = accumulate, add2 = accumulate && !second_store;
+        float* __restrict__ yo = yr + tb;
+        for (int n = threadIdx.x; n < N; n += SLICQ_SLICE_THREADS) {
+            const float2 z0 = Z[PF::slot(wo)];
+            wo = PF::step_out(wo, SLICQ_SLICE_THREADS);
+            const float2 z = make_float2(z0.x * scale, z0.y * scale);
+            if ((n < N / 2) ? add1 : add2) slicq_red_add2(yo + 2 * n, z); else *reinterpret_cast<float2*>(yo + 2 * n) = z;
+        }
+    } else {
+        for (int n = threadIdx.x; n < N; n += SLICQ_SLICE_THREADS) {
+            const float2 z0 = Z[PF::slot(wo)];
+            wo = PF::step_out(wo, SLICQ_SLICE_THREADS);
+            const float2 z = make_float2(z0.x * scale, z0.y * scale);
+            const bool first = n < N / 2;
+            const bool add = accumulate && (first || !second_store);
+            if (first && first_to_halo) {
+                if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
+            } else {
+                const long long t = tb + 2 * n;
+                if (t >= 0 && t < p.T) { if (add) slicq_red_add(yr + t, z.x); else yr[t] = z.x; }
+                if (t + 1 >= 0 && t + 1 < p.T) { if (add) slicq_red_add(yr + t + 1, z.y); else yr[t + 1] = z.y; }
+            }
         }
     }
     PHASE_MARK(6);

@@ -36,6 +36,14 @@ __device__ long long* g_bins_phase_buf = nullptr;   // this header is included b
 #define BINS_FLUSH(M_) do {} while (0)
 #endif
 
+// tuning experiment only (-DSLICQ_DEBUG_TWRAP=n): all units share n rows of the synthesis scratch, so that T
+// stays L2 resident (results are garbage; measures what an L2-resident intermediate would buy)
+#ifdef SLICQ_DEBUG_TWRAP
+#define SLICQ_TROW(u) ((long long)((u) % SLICQ_DEBUG_TWRAP))
+#else
+#define SLICQ_TROW(u) ((long long)(u))
+#endif
+
 struct JobCtx {
     int u0, u1;     // unit range of this job (indices local to the chunk)
     int F;          // bins in the bucket
@@ -183,7 +191,7 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
             const int fb = e / M, n = e - fb * M;
             const float2* src = sm + (g * j.F + fb) * PITCH + n;
             const float w0 = wsm[e], w1 = wsm[e + 1];
-            *reinterpret_cast<float4*>(p.spec + (long long)(base + g) * p.spec_stride + coff0 + e) =
+            *reinterpret_cast<float4*>(p.spec + SLICQ_TROW(base + g) * p.spec_stride + coff0 + e) =
                 make_float4(src[0].x * w0, src[0].y * w0, src[1].x * w1, src[1].y * w1);
         }
     }
@@ -314,7 +322,7 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             for (int n = 0; n < B; ++n) v[n] = src[n];
             dft<B, false>(v);
             const int off = c.y + k1;
-            float2* o = p.spec + (long long)(base + c.x) * p.spec_stride + off;
+            float2* o = p.spec + SLICQ_TROW(base + c.x) * p.spec_stride + off;
 #pragma unroll
             for (int k2 = 0; k2 < B; ++k2) {
                 const float w = __ldg(wi + off + A * k2);
@@ -448,7 +456,7 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             }
             const int coff = __ldg(p.t.bin_coff + j.first_bin + f) + r;
             const float wv = __ldg(p.t.wi + coff);
-            p.spec[(long long)(base + gs) * p.spec_stride + coff] = make_float2(y.x * wv, y.y * wv);
+            p.spec[SLICQ_TROW(base + gs) * p.spec_stride + coff] = make_float2(y.x * wv, y.y * wv);
         }
         __syncthreads();
     }
