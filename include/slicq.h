@@ -102,6 +102,20 @@ int slicq_forward_packed(const slicq_plan* plan, const float* x, int64_t n_rows,
                          int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
                          void* scratch, size_t scratch_bytes, void* stream);
 
+/* Analysis fused with the magnitude the model consumes (replaces the separate ComplexNorm pass,
+ * xumx_slicq_v2/transforms.py:181-208 called at separator.py:338,346 and training.py; abs_of_real_complex
+ * phase.py:116-118): besides the coefficients, norms[b] (fp32, logical shape [n_rows][F_b][S][M_b],
+ * strides in floats, M contiguous) receives |c| = sqrt(re^2 + im^2) from the epilogue of the per-bin
+ * transforms, so |X| costs 4 extra bytes per coefficient instead of an 8-byte read + 4-byte write pass. */
+int slicq_forward_norm(const slicq_plan* plan, const float* x, int64_t n_rows, int64_t x_row_stride,
+                       int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                       const slicq_bucket_view* buckets, const slicq_bucket_view* norms, void* scratch,
+                       size_t scratch_bytes, void* stream);
+/* packed variant: `norms` is ONE allocation of n_rows * n_slices * sum(M_j) floats, same bucket order */
+int slicq_forward_packed_norm(const slicq_plan* plan, const float* x, int64_t n_rows, int64_t x_row_stride,
+                              int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
+                              void* norms, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Synthesis.  y: [n_rows] rows, row r at y + r*y_row_stride, receives `length` samples whose
  * first one is global sample t0.  halo_out (optional, [n_rows][hop] float32) receives the part of
  * local slice 0 that belongs to the hop before this shard (only when k0 > 0). */

@@ -168,6 +168,22 @@ def test_masked_inverse_equals_plain_inverse_of_masked_coefficients(base):
     assert torch.equal(y, y_ref)
 
 
+def test_forward_with_norm_equals_complexnorm(base):
+    """|X| written by the analysis epilogue == ComplexNorm()(X) of the same call."""
+    from xumx_slicq_b200 import make_filterbanks, ComplexNorm
+    nsgt, _ = make_filterbanks(base)
+    x = torch.from_numpy(common.small_input()[:, :14000]).view(1, 2, -1).contiguous()
+    X_ref = nsgt(x)
+    X, Xmag = nsgt.forward_with_norm(x)
+    ref = ComplexNorm()(X_ref)
+    assert len(X) == len(Xmag) == len(ref)
+    for a, a_ref, m, m_ref in zip(X, X_ref, Xmag, ref):
+        assert torch.equal(a, a_ref)                         # the coefficients are untouched by the fusion
+        assert m.shape == m_ref.shape and m.dtype == torch.float32
+        scale = float(m_ref.max())
+        assert float((m - m_ref).abs().max()) <= 1e-6 * scale   # hypot vs sqrt(fma): a few ulp
+
+
 def test_inverse_autograd_is_the_exact_adjoint(base):
     """gradients through INSGT_SL.  The transform is linear, so the gradient of
     L = <S c, g> w.r.t. c must be S^T g: check <S c, g> == <c, S^T g> and a directional derivative."""

@@ -261,6 +261,21 @@ def test_masked_inverse_fused(base, dev):
     assert torch.equal(y, y_ref)
 
 
+def test_forward_with_norm_fused(base, dev):
+    """magnitudes from the analysis epilogue == ComplexNorm()(X); split and unsplit calls."""
+    from xumx_slicq_b200 import make_filterbanks, ComplexNorm
+    nsgt, _ = make_filterbanks(base)
+    for shape in ((1, 2, 100000), (4, 2, 1323000)):          # the second one takes the row-split path
+        x = torch.rand(*shape, device=dev) * 2 - 1
+        X_ref = nsgt(x)
+        X, Xmag = nsgt.forward_with_norm(x)
+        ref = ComplexNorm()(X_ref)
+        for a, a_ref, m, m_ref in zip(X, X_ref, Xmag, ref):
+            assert torch.equal(a, a_ref)
+            assert m.shape == m_ref.shape and m.dtype == torch.float32
+            assert float((m - m_ref).abs().max()) <= 1e-6 * float(m_ref.max())
+
+
 def test_inverse_autograd_adjoint(base, dev):
     """Gradients through INSGT_SL (SDR-loss training, training.py:83-95): exact adjoint on the GPU."""
     from xumx_slicq_b200 import make_filterbanks

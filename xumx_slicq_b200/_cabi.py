@@ -23,7 +23,7 @@ SLICQ_E_SCRATCH = -4
 EXPORTS = (
     "slicq_abi_version", "slicq_last_error", "slicq_plan_create", "slicq_plan_destroy",
     "slicq_plan_n_buckets", "slicq_plan_bucket_info", "slicq_plan_num_slices",
-    "slicq_scratch_bytes", "slicq_forward", "slicq_forward_packed", "slicq_inverse", "slicq_inverse_masked", "slicq_launch_count",
+    "slicq_scratch_bytes", "slicq_forward", "slicq_forward_packed", "slicq_forward_norm", "slicq_forward_packed_norm", "slicq_inverse", "slicq_inverse_masked", "slicq_launch_count",
     "slicq_profile_enable", "slicq_profile_read",
 )
 KERNEL_NAMES = ("slice_fft_fwd", "bins_fwd", "bins_inv", "slice_fft_inv")
@@ -74,6 +74,14 @@ def _declare(lib: C.CDLL) -> C.CDLL:
     lib.slicq_forward_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.slicq_forward_packed.restype = C.c_int
+    lib.slicq_forward_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_int64, C.POINTER(BucketViewC), C.POINTER(BucketViewC), C.c_void_p, C.c_size_t,
+                                       C.c_void_p]
+    lib.slicq_forward_norm.restype = C.c_int
+    lib.slicq_forward_packed_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                              C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_void_p]
+    lib.slicq_forward_packed_norm.restype = C.c_int
     lib.slicq_inverse.argtypes = [C.c_void_p, C.POINTER(BucketViewC), C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.slicq_inverse.restype = C.c_int
@@ -197,6 +205,20 @@ class Plan:
         _check(self.lib, self.lib.slicq_forward_packed(
             self.handle, C.c_void_p(x_ptr), n_rows, x_row_stride, n_samples, t0, k0, n_slices,
             C.c_void_p(coefs_ptr), C.c_void_p(scratch_ptr), scratch_bytes, C.c_void_p(stream)))
+
+    def forward_packed_norm(self, x_ptr: int, n_rows: int, x_row_stride: int, n_samples: int, t0: int, k0: int,
+                            n_slices: int, coefs_ptr: int, norms_ptr: int, scratch_ptr: int, scratch_bytes: int,
+                            stream: int):
+        _check(self.lib, self.lib.slicq_forward_packed_norm(
+            self.handle, C.c_void_p(x_ptr), n_rows, x_row_stride, n_samples, t0, k0, n_slices,
+            C.c_void_p(coefs_ptr), C.c_void_p(norms_ptr), C.c_void_p(scratch_ptr), scratch_bytes, C.c_void_p(stream)))
+
+    def forward_norm(self, x_ptr: int, n_rows: int, x_row_stride: int, n_samples: int, t0: int, k0: int,
+                     n_slices: int, views: Sequence[tuple], norm_views: Sequence[tuple], scratch_ptr: int,
+                     scratch_bytes: int, stream: int):
+        _check(self.lib, self.lib.slicq_forward_norm(
+            self.handle, C.c_void_p(x_ptr), n_rows, x_row_stride, n_samples, t0, k0, n_slices,
+            self._views(views), self._views(norm_views), C.c_void_p(scratch_ptr), scratch_bytes, C.c_void_p(stream)))
 
     def inverse(self, views: Sequence[tuple], n_rows: int, n_slices: int, k0: int, y_ptr: int, y_row_stride: int,
                 length: int, t0: int, halo_ptr: int, scratch_ptr: int, scratch_bytes: int, stream: int):

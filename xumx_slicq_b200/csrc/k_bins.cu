@@ -72,6 +72,7 @@ SLICQ_DEVFN void bins_body(const SlicqBinsParams& p, unsigned char* smem) {
     if (j.u1 > p.n_rs) j.u1 = p.n_rs;
     if (j.u0 >= j.u1) return;
     j.F = b.n_bins; j.gt = b.gt; j.first_bin = b.first_bin; j.rs0 = p.rs0; j.S = p.S; j.x_rows = SYNTH ? p.x_rows : 0;
+    j.aux = SYNTH ? (b.mptr != nullptr) : (b.nptr != nullptr);
     switch (b.M) {
 #define SLICQ_FFT_SIZE(M_, K_, A_, B_) \
     case M_: JobRunner<M_, K_, A_, B_, SYNTH>::run(p, b, j, smem); break;

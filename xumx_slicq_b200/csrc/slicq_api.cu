@@ -458,7 +458,7 @@ extern "C" size_t slicq_scratch_bytes(const slicq_plan* p, int64_t n_rows, int64
 
 namespace {
 int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqBinsParams& bp, int n_rs,
-                     const slicq_bucket_view* masks = nullptr) {
+                     const slicq_bucket_view* masks = nullptr, const slicq_bucket_view* norms = nullptr) {
     int jobs = 0;
     bp.n_buckets = (int)p->buckets.size();
     double total = 0.0;
@@ -470,7 +470,9 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
         a.s_row = views[i].s_row; a.s_bin = views[i].s_bin; a.s_slice = views[i].s_slice;
         a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.gt = b.gt; a.tw_off = b.tw_off;
         a.mptr = masks ? reinterpret_cast<const float*>(masks[i].ptr) : nullptr;
-        a.ms_row = masks ? masks[i].s_row : 0; a.ms_bin = masks ? masks[i].s_bin : 0; a.ms_slice = masks ? masks[i].s_slice : 0;
+        a.nptr = norms ? reinterpret_cast<float*>(norms[i].ptr) : nullptr;
+        const slicq_bucket_view* aux = masks ? masks : norms;      // synthesis masks or analysis magnitudes: never both
+        a.ms_row = aux ? aux[i].s_row : 0; a.ms_bin = aux ? aux[i].s_bin : 0; a.ms_slice = aux ? aux[i].s_slice : 0;
         if (p->only_bucket >= 0 && (int)i != p->only_bucket) {       // tuning aid: time one bucket alone
             a.units_per_job = b.gt; a.n_jobs = 0; a.job_start = jobs;
             continue;
@@ -492,7 +494,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
 namespace {
 int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
                 int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
-                const slicq_bucket_view* buckets, void* scratch, cudaStream_t s);
+                const slicq_bucket_view* buckets, const slicq_bucket_view* norms, void* scratch, cudaStream_t s);
 int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const slicq_bucket_view* masks, int64_t x_rows,
                 int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
                 int64_t t0, float* halo_out, void* scratch, cudaStream_t s);
@@ -517,31 +519,53 @@ int run_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse
 }
 }  // namespace
 
-extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
-                             int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
-                             const slicq_bucket_view* buckets, void* scratch, size_t scratch_bytes, void* stream) {
+namespace {
+int forward_impl(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                 int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                 const slicq_bucket_view* buckets, const slicq_bucket_view* norms, void* scratch, size_t scratch_bytes,
+                 void* stream) {
     if (!p || !x || !buckets) return fail(SLICQ_E_INVALID, "null argument");
     if (n_rows <= 0 || n_slices <= 0 || n_samples < 0) return fail(SLICQ_E_INVALID, "bad shape");
     if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
     if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 0) || !scratch)
         return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
     for (size_t i = 0; i < p->buckets.size(); ++i)
-        if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
+        if (!buckets[i].ptr || (norms && !norms[i].ptr)) return fail(SLICQ_E_INVALID, "null bucket pointer");
     cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
     if (use_split(p, n_rows, n_slices)) {
         return run_split(p, n_rows, n_slices, 0, scratch, s0, [&](int64_t r0, int64_t rows, void* scr, cudaStream_t st) {
-            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size());
+            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size()), nv;
             for (auto& b : v) b.ptr = reinterpret_cast<float2*>(b.ptr) + r0 * b.s_row;
-            return forward_one(p, x + r0 * x_row_stride, rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(), scr, st);
+            if (norms) {
+                nv.assign(norms, norms + p->buckets.size());
+                for (auto& b : nv) b.ptr = reinterpret_cast<float*>(b.ptr) + r0 * b.s_row;
+            }
+            return forward_one(p, x + r0 * x_row_stride, rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(),
+                               norms ? nv.data() : nullptr, scr, st);
         });
     }
-    return forward_one(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, buckets, scratch, s0);
+    return forward_one(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, buckets, norms, scratch, s0);
+}
+}  // namespace
+
+extern "C" int slicq_forward(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                             int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                             const slicq_bucket_view* buckets, void* scratch, size_t scratch_bytes, void* stream) {
+    return forward_impl(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, buckets, nullptr, scratch, scratch_bytes, stream);
+}
+
+extern "C" int slicq_forward_norm(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                                  int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
+                                  const slicq_bucket_view* buckets, const slicq_bucket_view* norms, void* scratch,
+                                  size_t scratch_bytes, void* stream) {
+    if (!norms) return fail(SLICQ_E_INVALID, "norms missing");
+    return forward_impl(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, buckets, norms, scratch, scratch_bytes, stream);
 }
 
 namespace {
 int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
                 int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices,
-                const slicq_bucket_view* buckets, void* scratch, cudaStream_t s) {
+                const slicq_bucket_view* buckets, const slicq_bucket_view* norms, void* scratch, cudaStream_t s) {
     const long long units = n_rows * n_slices, cu = chunk_units(p, 0);
     float2* H = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
     SlicqSliceParams sp;
@@ -558,7 +582,7 @@ int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_r
         ++g_launches;
         if (rc) break;
         bp->n_rs = n; bp->rs0 = (int)u0;
-        const int jobs = fill_bins_params(p, buckets, *bp, n);
+        const int jobs = fill_bins_params(p, buckets, *bp, n, nullptr, norms);
         { ProfScope ps(K_BINS_FWD, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 0, s); }
         ++g_launches;
     }
@@ -573,21 +597,40 @@ int forward_one(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_r
 }  // namespace
 
 // Canonical packed layout: all buckets in one allocation, bucket b = contiguous [n_rows][F_b][S][M_b].
-extern "C" int slicq_forward_packed(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
-                                    int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
-                                    void* scratch, size_t scratch_bytes, void* stream) {
-    if (!p || !coefs) return fail(SLICQ_E_INVALID, "null argument");
+namespace {
+// canonical packed layout: bucket b = contiguous [n_rows][F_b][S][M_b] elements of `elem` bytes, buckets in order
+std::vector<slicq_bucket_view> packed_views(const slicq_plan* p, void* base_, int64_t n_rows, int64_t n_slices, size_t elem) {
     std::vector<slicq_bucket_view> v(p->buckets.size());
-    unsigned char* base = reinterpret_cast<unsigned char*>(coefs);
+    unsigned char* base = reinterpret_cast<unsigned char*>(base_);
     for (size_t i = 0; i < p->buckets.size(); ++i) {
         const Bucket& b = p->buckets[i];
         v[i].ptr = base;
         v[i].s_slice = b.M;
         v[i].s_bin = (int64_t)n_slices * b.M;
         v[i].s_row = (int64_t)b.n_bins * n_slices * b.M;
-        base += (size_t)n_rows * b.n_bins * n_slices * b.M * 8;
+        base += (size_t)n_rows * b.n_bins * n_slices * b.M * elem;
     }
+    return v;
+}
+}  // namespace
+
+// Canonical packed layout: all buckets in one allocation, bucket b = contiguous [n_rows][F_b][S][M_b].
+extern "C" int slicq_forward_packed(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                                    int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
+                                    void* scratch, size_t scratch_bytes, void* stream) {
+    if (!p || !coefs) return fail(SLICQ_E_INVALID, "null argument");
+    std::vector<slicq_bucket_view> v = packed_views(p, coefs, n_rows, n_slices, 8);
     return slicq_forward(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(), scratch, scratch_bytes, stream);
+}
+
+extern "C" int slicq_forward_packed_norm(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_row_stride,
+                                         int64_t n_samples, int64_t t0, int64_t k0, int64_t n_slices, void* coefs,
+                                         void* norms, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!p || !coefs || !norms) return fail(SLICQ_E_INVALID, "null argument");
+    std::vector<slicq_bucket_view> v = packed_views(p, coefs, n_rows, n_slices, 8);
+    std::vector<slicq_bucket_view> nv = packed_views(p, norms, n_rows, n_slices, 4);
+    return slicq_forward_norm(p, x, n_rows, x_row_stride, n_samples, t0, k0, n_slices, v.data(), nv.data(), scratch,
+                              scratch_bytes, stream);
 }
 
 namespace {

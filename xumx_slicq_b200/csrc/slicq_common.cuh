@@ -212,7 +212,10 @@ struct SlicqBucketArg {
     // fused mask*mix synthesis (slicq_inverse_masked): fp32 mask of the same logical shape as the
     // OUTPUT rows [targets*rows][F][S][M]; null = plain synthesis
     const float* mptr;
-    long long ms_row, ms_bin, ms_slice;
+    // fused magnitude (slicq_forward_norm, reference: ComplexNorm transforms.py:181-208 /
+    // abs_of_real_complex phase.py:116-118): analysis also writes |c| as fp32 [rows][F][S][M]; null = off
+    float* nptr;
+    long long ms_row, ms_bin, ms_slice;   // element strides of the mask (synthesis) / magnitude (analysis) tensor
 };
 
 struct SlicqBinsParams {

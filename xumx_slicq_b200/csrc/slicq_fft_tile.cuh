@@ -51,6 +51,7 @@ struct JobCtx {
     int first_bin;
     int rs0, S;     // chunk origin and slices per row: unit g is (row, k) = divmod(rs0 + g, S)
     int x_rows;     // masked synthesis: mixture rows (0 = plain)
+    bool aux;       // a second tensor (synthesis: mask, analysis: magnitude output) is addressed through ms_*
 };
 
 SLICQ_DEVFN float2 cneg_if(float2 v, bool neg) { return neg ? make_float2(-v.x, -v.y) : v; }
@@ -68,10 +69,11 @@ SLICQ_DEVFN void fill_slot_off(long long* so, const SlicqBucketArg& b, const Job
         const int row = rs / j.S, k = rs - row * j.S;
         const int rowx = j.x_rows ? row % j.x_rows : row;
         so[t] = rowx * b.s_row + f * b.s_bin + k * b.s_slice;
-        if (j.x_rows) so[256 + t] = row * b.ms_row + f * b.ms_bin + k * b.ms_slice;
+        if (j.aux) so[256 + t] = row * b.ms_row + f * b.ms_bin + k * b.ms_slice;
     }
 }
 SLICQ_DEVFN float2 cscale(float2 v, float s) { return make_float2(v.x * s, v.y * s); }
+SLICQ_DEVFN float cmag(float2 v) { return sqrtf(fmaf(v.x, v.x, v.y * v.y)); }
 
 // =========================================================================================
 // kind 1
@@ -127,7 +129,9 @@ SLICQ_DEVFN void ana_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
         __syncthreads();
         for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
             const int slot = t / M, n = t - slot * M;
-            b.ptr[so[slot] + n] = sm[slot * PITCH + n];
+            const float2 c = sm[slot * PITCH + n];
+            b.ptr[so[slot] + n] = c;
+            if (b.nptr != nullptr) b.nptr[so[256 + slot] + n] = cmag(c);
         }
         __syncthreads();
     }
@@ -257,6 +261,11 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             float2* o = b.ptr + so[slot] + k1;
 #pragma unroll
             for (int k2 = 0; k2 < B; ++k2) o[A * k2] = cneg_if(v[k2], (A * k2) & 1);
+            if (b.nptr != nullptr) {
+                float* on = b.nptr + so[256 + slot] + k1;
+#pragma unroll
+                for (int k2 = 0; k2 < B; ++k2) on[A * k2] = cmag(v[k2]);
+            }
         }
         BINS_T(t3_);
         __syncthreads();
@@ -388,6 +397,11 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             float2* o = b.ptr + so[slot] + k1;
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2) o[P * k2] = cneg_if(v[k2], k2 & 1);   // P odd: (-1)^(P k2) = (-1)^k2
+            if (b.nptr != nullptr) {
+                float* on = b.nptr + so[256 + slot] + k1;
+#pragma unroll
+                for (int k2 = 0; k2 < R; ++k2) on[P * k2] = cmag(v[k2]);
+            }
         }
         __syncthreads();
     }

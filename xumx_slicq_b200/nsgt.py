@@ -177,6 +177,23 @@ class NSGT_sliced(torch.nn.Module):
             o += n
         return slab, out
 
+    def alloc_norms(self, n_rows: int, n_slices: int, device, lead=None) -> tuple:
+        """One float32 slab for the magnitudes of all buckets, same bucket order / packing as the
+        coefficients.  Returns (slab, [bucket tensors [*lead, F, S, M]])."""
+        t = self.tables
+        slab = torch.empty(n_rows * n_slices * t.sum_M, dtype=torch.float32, device=device)
+        out, o = [], 0
+        lead = tuple(lead) if lead is not None else (n_rows,)
+        for (_, nb, M) in t.buckets:
+            inner = (n_slices * M, M, 1)                       # strides of [F,S,M]
+            st, acc = [], nb * n_slices * M
+            for d in reversed(lead):
+                st.append(acc)
+                acc *= d
+            out.append(slab.as_strided(lead + (nb, n_slices, M), tuple(reversed(st)) + inner, o))
+            o += n_rows * nb * n_slices * M
+        return slab, out
+
     @staticmethod
     def _view_of(c: torch.Tensor) -> tuple:
         """(ptr, s_row, s_bin, s_slice) of a complex [N,F,S,M] tensor with contiguous M."""
@@ -184,8 +201,11 @@ class NSGT_sliced(torch.nn.Module):
 
     # -- analysis ---------------------------------------------------------------------------
     def forward_rows(self, x: torch.Tensor, k0: int = 0, n_slices: int | None = None, t0: int = 0,
-                     lead=None, as_real: bool = False) -> List[torch.Tensor]:
+                     lead=None, as_real: bool = False, with_norm: bool = False):
         """x [N, T] float32 -> list of contiguous [N, F_b, S, M_b] complex64 (canonical layout).
+
+        ``with_norm``: also return the magnitudes |c| (list of float32 [*lead, F_b, S, M_b]) written by
+        the same kernels (fused ComplexNorm, transforms.py:181-208): returns (coefficients, norms).
 
         ``k0 / n_slices / t0`` select a slice range of a longer signal (shard of a long track):
         local slice i is global slice k0+i and x[:, 0] is global sample t0."""
@@ -203,6 +223,11 @@ class NSGT_sliced(torch.nn.Module):
             slab, out = self.alloc_coefficients(N, S, x.device, lead=lead, as_real=as_real)
             nbytes = plan.scratch_bytes(N, S, False)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            if with_norm:
+                nslab, norms = self.alloc_norms(N, S, x.device, lead=lead)
+                plan.forward_packed_norm(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S, slab.data_ptr(),
+                                         nslab.data_ptr(), scratch.data_ptr(), nbytes, _BACKEND.stream(x.device))
+                return out, norms
             plan.forward_packed(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S, slab.data_ptr(),
                                 scratch.data_ptr(), nbytes, _BACKEND.stream(x.device))
         return out

@@ -92,6 +92,18 @@ class NSGT_SL(nn.Module):
         x = x.contiguous().view(-1, shape[-1])
         return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True)
 
+    def forward_with_norm(self, x: Tensor):
+        """(X, |X|) in one pass: ``X`` exactly as :meth:`forward`, ``|X|`` what ``ComplexNorm()(X)`` returns
+        (list of [..., F_b, S, M_b]); the magnitude is written by the epilogue of the analysis kernels
+        instead of a separate pass over the coefficients (reference call sites: separator.py:338,346,
+        model.py via abs_of_real_complex phase.py:116-118).  Extra entry point: :meth:`forward` is unchanged."""
+        shape = x.size()
+        dev = _module_device(self.nsgt)
+        if x.device != dev and x.device.type == "cpu":
+            x = x.to(dev)
+        x = x.contiguous().view(-1, shape[-1])
+        return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True, with_norm=True)
+
 
 class _InverseFn(torch.autograd.Function):
     """Differentiable synthesis: forward = INSGT kernels, backward = their exact adjoint on the
