@@ -283,10 +283,10 @@ template <class PF>
 __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
     constexpr int N = PF::N;
-    const int rsl = blockIdx.x;
-    const int rs = p.rs0 + rsl;
-    const int row = rs / p.S, k = rs - row * p.S;
-    if ((k & 1) != p.parity) return;
+    // CTA i of the launch = i-th slice of this launch's parity at or after unit rs0
+    const int pi = p.par_base + blockIdx.x;
+    const int row = pi / p.par_cs, k = 2 * (pi - row * p.par_cs) + p.parity;
+    const int rsl = row * p.S + k - p.rs0;
     PHASE_MARK(0);
     // ---- gather of the windowed bin spectra + Hermitian pre-processing.
     // Spectrum position f is the sum over the bins j = jlo .. jlo + n (n <= 3) covering it of
@@ -467,7 +467,14 @@ extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s)
     const int smem = slice_inv_smem_bytes(p->t);
     static int attr_done = 0;
     if (attr_done < smem) { SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem); attr_done = smem; }
-    SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
+    // slices of parity q among units [0, u) of rows of S slices
+    const int S = p->S, q = p->parity, cs = (S + 1 - q) / 2;
+    auto count = [&](long long u) { return (u / S) * cs + ((u % S) + 1 - q) / 2; };
+    const long long c0 = count(p->rs0), c1 = count((long long)p->rs0 + p->n_rs);
+    if (c1 <= c0) return 0;
+    SlicqSliceParams sp = *p;
+    sp.par_cs = cs; sp.par_base = (int)c0;
+    SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3((unsigned)(c1 - c0)), dim3(SLICQ_SLICE_THREADS), smem, s, sp);
     return (int)cudaGetLastError();
 }
 

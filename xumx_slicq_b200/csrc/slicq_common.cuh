@@ -243,5 +243,6 @@ struct SlicqSliceParams {
     long long spec_stride;
     float* halo_out;       // inverse: [rows][hop] or null; first half of local slice 0 when k0 > 0
     int n_rs, rs0, S;
-    int parity;            // inverse: this launch handles slices with (k & 1) == parity
+    int parity;            // inverse: this launch handles slices with (k & 1) == parity ...
+    int par_cs, par_base;  // ... one CTA each: par_cs = such slices per row, par_base = how many precede unit rs0 (set by the launcher)
 };
