@@ -340,13 +340,13 @@ def main():
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     achieved = alg_step / (ms_per_step * 1e-3) / 1e9
     # DRAM bytes per (row, slice) unit from the committed ncu --set full capture (profiles/r1_ncu_summary.txt,
-    # dram__bytes_read.sum + dram__bytes_write.sum, batch 2): analysis 49.8 + 213.2 KB, synthesis 302.6 + 226.3 KB
-    traffic_step = int((49.8e3 + 213.2e3) * units_f + (302.6e3 + 226.3e3) * units_i)
+    # dram__bytes_read.sum + dram__bytes_write.sum, batch 2): analysis 50.2 + 214.2 KB, synthesis 302.8 + 216.8 KB
+    traffic_step = int((50.2e3 + 214.2e3) * units_f + (302.8e3 + 216.8e3) * units_i)
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic_step,
         "traffic_note": "per step, scaled per unit from the ncu capture in profiles/ (scratch spectra round-trip "
-                        "through HBM at the default chunk size: 2.9x the algorithmic bytes on the synthesis side)",
+                        "through HBM at the default chunk size: 2.8x the algorithmic bytes on the synthesis side)",
         "scope": "whole path: algorithmic bytes of one step (185 240 B per (row,slice) and direction) / "
                  "CUDA-event time of the step (all five kernels)",
         "peak_source": peak_src, "algorithmic_bytes_per_step": alg_step,
