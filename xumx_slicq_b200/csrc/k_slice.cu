@@ -6,8 +6,8 @@
 // with the Good-Thomas prime-factor algorithm on the 3-D index space 43 x 15 x 14: the three
 // factors are pairwise coprime, so there are NO twiddle multiplications between the passes --
 // input index n lives at (n mod 43, n mod 15, n mod 14), output index
-// k = (210 k1 + 602 k2 + 645 k3) mod 9030 lives at (k1, k2, k3).  Both maps are precomputed
-// (perm_in / perm_out, 18 KB each, L1/L2 resident) so the kernels do no modular arithmetic.
+// k = (210 k1 + 602 k2 + 645 k3) mod 9030 lives at (k1, k2, k3).  The load / store phases visit
+// indices tid + i * blockDim and keep the three residues of the index in registers (Pfa3::Walk).
 //   pass A  43-point symmetric real half-transforms down the first axis (rdft_sym<43>), the real
 //           and the imaginary part of a column on separate threads, in place
 //   pass B  combine (A_k -/+ i B_k) fused with the 15-point codelet, rows k1 and 43-k1 together
@@ -23,8 +23,6 @@
 //            nsgt/unslicing.py:33-69 + nsgt/slicq.py:207-230 (inverse); closed forms in DESIGN.md.
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
-#include <cstdio>
-#include <cstdlib>
 
 // optional per-phase timing (tuning builds only, -DSLICQ_PHASE_TIMING): thread 0 of every CTA stores
 // clock64() at the phase boundaries into a buffer registered with slicq_debug_set_timing()
@@ -95,9 +93,6 @@ struct Pfa3 {
     }
     static SLICQ_DEVFN int slot(Walk w) { return w.a * SA + w.b * SB + w.c; }
 };
-#define POS_IN(n) PF::pos_in(n)
-#define POS_OUT(k) PF::pos_out(k)
-
 template <class PF, bool INV>
 SLICQ_DEVFN void pfa_passes(float2* Z) {
     constexpr int P1 = PF::P1, P2 = PF::P2, P3 = PF::P3, SA = PF::SA, SB = PF::SB;
@@ -301,7 +296,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     float2* RN = reinterpret_cast<float2*>(gd + ((p.t.n_bins + 4 + 3) & ~3));
     const int tid = threadIdx.x;
     constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = SLICQ_GATHER_UG, NR = (NW + UG - 1) / UG;
-    #ifdef SLICQ_DEBUG_TWRAP
+#ifdef SLICQ_DEBUG_TWRAP
     const float2* __restrict__ Trow = p.spec + (long long)(rsl % SLICQ_DEBUG_TWRAP) * p.spec_stride;   // tuning experiment, see slicq_fft_tile.cuh
 #else
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
@@ -366,13 +361,13 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     load_round(0);
     if (xe.x >= 0) {
         const float2 e = make_float2(x2.x + x3.x, x2.y + x3.y);
-        if (xe.x < N) Z[POS_IN(xe.x)] = e; else *RN = e;
+        if (xe.x < N) Z[PF::pos_in(xe.x)] = e; else *RN = e;
     }
     for (int i = tid + NT; i < nx; i += NT) {
         const int4 q = __ldg(p.t.gx + i);
         float2 e = __ldg(Trow + q.y);
         if (q.z >= 0) { const float2 v = __ldg(Trow + q.z); e.x += v.x; e.y += v.y; }
-        if (q.x < N) Z[POS_IN(q.x)] = e; else *RN = e;
+        if (q.x < N) Z[PF::pos_in(q.x)] = e; else *RN = e;
     }
     __syncthreads();
 #pragma unroll
@@ -438,17 +433,6 @@ static int slice_inv_smem_bytes(const SlicqDeviceTables& t) {
     b += (size_t)((t.n_bins + 4 + 3) & ~3) * sizeof(int);
     b += 2 * sizeof(float2);
     return (int)b;
-}
-
-// fills perm_in[N] and perm_out[N+1] for slice length L (host)
-extern "C" int slicq_slice_perm(int L, unsigned short* perm_in, unsigned short* perm_out) {
-    if (L != 2 * Pfa9030::N) return -1;
-    for (int n = 0; n < Pfa9030::N; ++n) {
-        perm_in[n] = (unsigned short)Pfa9030::pos_in(n);
-        perm_out[n] = (unsigned short)Pfa9030::pos_out(n);
-    }
-    perm_out[Pfa9030::N] = perm_out[0];
-    return 0;
 }
 
 extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s) {

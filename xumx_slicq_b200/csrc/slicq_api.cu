@@ -54,7 +54,6 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s);
 extern "C" int slicq_slice_smem_bytes(int L);
 extern "C" int slicq_bins_threads(void);
-extern "C" int slicq_slice_perm(int L, unsigned short* perm_in, unsigned short* perm_out);
 
 namespace {
 
@@ -335,12 +334,6 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     for (int k = 0; k <= p->N2 / 2; ++k) gjp[k] = gj[k] | (gj[p->N2 - k] << 16);
     const int n_gx = (int)gx.size();
     if (gx.empty()) gx.push_back(int4{-1, 0, -1, 0});
-    std::vector<unsigned short> perm_in(p->N2), perm_out(p->N2 + 1);
-    if (slicq_slice_perm(L, perm_in.data(), perm_out.data()) != 0) {
-        delete p;
-        return fail(SLICQ_E_UNSUPPORTED, "no slice-FFT permutation for this slice length");
-    }
-
     SlicqDeviceTables& d = p->dev;
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
@@ -361,8 +354,6 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(gd, &d.gd, p->owned);
     rc |= upload(gx, &d.gx, p->owned);
     d.n_gx = n_gx;
-    rc |= upload(perm_in, &d.perm_in, p->owned);
-    rc |= upload(perm_out, &d.perm_out, p->owned);
     if (rc) {
         slicq_plan_destroy(p);
         return fail(SLICQ_E_CUDA, "device table upload failed");

@@ -80,72 +80,15 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 #define SLICQ_DEVFN __device__ __forceinline__
 
 // ---------------------------------------------------------------------------------------
-// asynchronous bulk copies (TMA 1-D, `cp.async.bulk`) completing on shared-memory mbarriers.
-// Protocol used by the kernels: the producer thread calls slicq_mbar_expect(bar, bytes), then any
-// number of slicq_bulk_g2s(...) whose sizes add up to `bytes`, then slicq_mbar_commit(bar);
-// consumers call slicq_mbar_wait(bar, parity).  On the GPU `expect` is the arriving operation and
-// `commit` compiles to nothing; the host emulation copies synchronously and arrives in `commit`.
+// fire-and-forget additions to global memory (no return value, performed at L2): the odd slices of the
+// synthesis add into samples an even slice has stored, without a read-modify-write round trip
 #ifdef SLICQ_EMU
-#include <atomic>
-#include <thread>
-struct SlicqMbar { std::atomic<int> phase; std::atomic<int> pending; int count; int pad_; };
-static inline void slicq_mbar_init(SlicqMbar* b, int count) { b->phase.store(0); b->pending.store(count); b->count = count; }
-static inline void slicq_mbar_init_fence() {}
-static inline void slicq_mbar_arrive(SlicqMbar* b) {
-    if (b->pending.fetch_sub(1) == 1) { b->pending.store(b->count); b->phase.fetch_xor(1); }
-}
-static inline void slicq_mbar_expect(SlicqMbar*, unsigned) {}
-static inline void slicq_mbar_commit(SlicqMbar* b) { slicq_mbar_arrive(b); }
-static inline void slicq_mbar_wait(SlicqMbar* b, int parity) { while (b->phase.load() == parity) std::this_thread::yield(); }
-static inline void slicq_bulk_g2s(void* dst, const void* src, unsigned bytes, SlicqMbar*) { memcpy(dst, src, bytes); }
-static inline void slicq_prefetch_l2(const void*, unsigned) {}
 static inline void slicq_red_add(float* p, float v) { *p += v; }
 static inline void slicq_red_add2(float* p, float2 v) { p[0] += v.x; p[1] += v.y; }
-// "one arrival per warp": the emulated threads are not lock-stepped, so every thread arrives
-#define SLICQ_WARP_ARRIVALS(nthreads) ((int)(nthreads))
-static inline void slicq_warp_arrive(SlicqMbar* b) { slicq_mbar_arrive(b); }
 #else
-struct __align__(8) SlicqMbar { unsigned long long v; };
-SLICQ_DEVFN unsigned slicq_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-SLICQ_DEVFN void slicq_mbar_init(SlicqMbar* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(slicq_smem_u32(b)), "r"(count) : "memory");
-}
-SLICQ_DEVFN void slicq_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-SLICQ_DEVFN void slicq_mbar_arrive(SlicqMbar* b) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(slicq_smem_u32(b)) : "memory");
-}
-SLICQ_DEVFN void slicq_mbar_expect(SlicqMbar* b, unsigned bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(slicq_smem_u32(b)), "r"(bytes) : "memory");
-}
-SLICQ_DEVFN void slicq_mbar_commit(SlicqMbar*) {}
-SLICQ_DEVFN void slicq_mbar_wait(SlicqMbar* b, int parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(slicq_smem_u32(b)), "r"(parity) : "memory");
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
-SLICQ_DEVFN void slicq_bulk_g2s(void* dst, const void* src, unsigned bytes, SlicqMbar* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(slicq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(slicq_smem_u32(b)) : "memory");
-}
-// asynchronous prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address into L2
-SLICQ_DEVFN void slicq_prefetch_l2(const void* src, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-// fire-and-forget additions to global memory (no return value, performed at L2)
 SLICQ_DEVFN void slicq_red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 SLICQ_DEVFN void slicq_red_add2(float* p, float2 v) {   // p 8-byte aligned
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-// all lanes of the warp are done with a stage: one arrival per warp
-#define SLICQ_WARP_ARRIVALS(nthreads) ((int)(nthreads) >> 5)
-SLICQ_DEVFN void slicq_warp_arrive(SlicqMbar* b) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) slicq_mbar_arrive(b);
 }
 #endif
 
@@ -191,8 +134,6 @@ struct SlicqDeviceTables {
     const int* gd;                // [J]       coff_j - pos_j + M_j / 2
     const int4* gx;               // [n_gx]    positions covered by 3 or 4 bins: {f, offset of the 3rd term, of the 4th or -1, 0}
     int n_gx;
-    const unsigned short* perm_in;   // [N2]     shared-memory slot of FFT input index n
-    const unsigned short* perm_out;  // [N2 + 1] shared-memory slot of FFT output index k (entry N2 == entry 0)
 };
 
 // one bucket as a kernel sees it for one call (pointer + strides of the caller's tensor)
