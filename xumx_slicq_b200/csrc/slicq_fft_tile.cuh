@@ -43,6 +43,12 @@ __device__ long long* g_bins_phase_buf = nullptr;   // this header is included b
 #else
 #define SLICQ_TROW(u) ((long long)(u))
 #endif
+// same idea for the caller's coefficients (-DSLICQ_DEBUG_CWRAP=n): the synthesis reads the first n units over and over
+#ifdef SLICQ_DEBUG_CWRAP
+#define SLICQ_CUNIT(u) ((u) % SLICQ_DEBUG_CWRAP)
+#else
+#define SLICQ_CUNIT(u) (u)
+#endif
 
 struct JobCtx {
     int u0, u1;     // unit range of this job (indices local to the chunk)
@@ -65,7 +71,7 @@ SLICQ_DEVFN float2 cneg_if(float2 v, bool neg) { return neg ? make_float2(-v.x, 
 SLICQ_DEVFN void fill_slot_off(long long* so, const SlicqBucketArg& b, const JobCtx& j, int base, int ng) {
     for (int t = threadIdx.x; t < ng * j.F; t += blockDim.x) {
         const int gs = t / j.F, f = t - gs * j.F;
-        const int rs = j.rs0 + base + gs;
+        const int rs = SLICQ_CUNIT(j.rs0 + base + gs);
         const int row = rs / j.S, k = rs - row * j.S;
         const int rowx = j.x_rows ? row % j.x_rows : row;
         so[t] = rowx * b.s_row + f * b.s_bin + k * b.s_slice;
@@ -303,7 +309,7 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int g = base + gs1;
         if (act1 && g < j.u1) {
-            const int rs = j.rs0 + g;
+            const int rs = SLICQ_CUNIT(j.rs0 + g);
             const int row = rs / j.S, k = rs - row * j.S;
             const int rowx = j.x_rows ? row % j.x_rows : row;
             const float2* src = b.ptr + rowx * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
