@@ -25,12 +25,18 @@
 #if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
 __device__ long long* g_bins_phase_buf = nullptr;   // this header is included by k_bins.cu only
 #define BINS_T(v) const long long v = clock64()
+#define BINS_T0(v) long long v = 0
+#define BINS_SET(v) v = clock64()
+#define BINS_COUNT() do { if (threadIdx.x == 0) ++bins_iters_; } while (0)
 #define BINS_ACC(i, a, b) do { if (threadIdx.x == 0) bins_acc_[i] += (b) - (a); } while (0)
-#define BINS_DECL long long bins_acc_[6] = {0, 0, 0, 0, 0, 0}
+#define BINS_DECL long long bins_acc_[6] = {0, 0, 0, 0, 0, 0}; long long bins_iters_ = 0
 #define BINS_FLUSH(M_) do { if (threadIdx.x == 0 && g_bins_phase_buf) { long long* o = g_bins_phase_buf + (long long)blockIdx.x * 8; \
-        for (int q_ = 0; q_ < 6; ++q_) o[q_] = bins_acc_[q_]; o[6] = (M_); o[7] = 1; } } while (0)
+        for (int q_ = 0; q_ < 6; ++q_) o[q_] = bins_acc_[q_]; o[6] = (M_) | (bins_iters_ << 16); o[7] = 1; } } while (0)
 #else
 #define BINS_T(v) do {} while (0)
+#define BINS_T0(v) do {} while (0)
+#define BINS_SET(v) do {} while (0)
+#define BINS_COUNT() do {} while (0)
 #define BINS_ACC(i, a, b) do {} while (0)
 #define BINS_DECL do {} while (0)
 #define BINS_FLUSH(M_) do {} while (0)
@@ -233,7 +239,14 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
     float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
-    const float2* __restrict__ tw = p.t.tw + b.tw_off + 0;
+    // the job's twiddles, transposed to [k1][n2], in shared memory behind the stage (immediate offsets in pass 1)
+    float2* twsm = sm + j.gt * j.F * PER;
+    {
+        const float2* __restrict__ tw = p.t.tw + b.tw_off;
+        for (int t = tid; t < M; t += blockDim.x) { const int k1 = t / B, c2 = t - k1 * B; twsm[t] = __ldg(tw + c2 * k1); }
+    }
+    const float2* twp = twsm + n2;
+    __syncthreads();
     BINS_DECL;
     for (int base = j.u0; base < j.u1; base += j.gt) {
         BINS_T(t0_);
@@ -252,7 +265,7 @@ SLICQ_DEVFN void ana_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             y1[0] = v[0];
 #pragma unroll
             for (int k1 = 1; k1 < A; ++k1)
-                y1[k1 * BP] = cneg_if(cmul_conj(v[k1], __ldg(tw + n2 * k1)), k1 & 1);  // (-1)^k1 folded here
+                y1[k1 * BP] = cneg_if(cmul_conj(v[k1], twp[k1 * B]), k1 & 1);  // (-1)^k1 folded here
         }
         BINS_T(t1_);
         __syncthreads();
@@ -303,10 +316,23 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
         sc[t] = make_int2(gs, __ldg(p.t.bin_coff + j.first_bin + f));
     }
     float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
-    const float2* __restrict__ tw = p.t.tw + b.tw_off;
-    const float* __restrict__ wi = p.t.wi;
+    // The job's twiddles, transposed to [k1][n2], and the bucket's dual windows live in shared memory
+    // behind the stage: pass 1 / pass 2 read them at immediate offsets instead of computing global
+    // addresses and waiting for L1 / L2 between the codelet and the stores.
+    float2* twsm = sm + j.gt * j.F * PER;
+    float* wsm = reinterpret_cast<float*>(twsm + M);
+    const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
+    {
+        const float2* __restrict__ tw = p.t.tw + b.tw_off;
+        for (int t = tid; t < M; t += blockDim.x) { const int k1 = t / B, c2 = t - k1 * B; twsm[t] = __ldg(tw + c2 * k1); }
+        for (int t = tid; t < j.F * M; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff_first + t);
+    }
+    const float2* twp = twsm + n2;
     __syncthreads();
+    BINS_DECL;
     for (int base = j.u0; base < j.u1; base += j.gt) {
+        BINS_T(t0_);
+        BINS_T0(tl_);
         const int g = base + gs1;
         if (act1 && g < j.u1) {
             const int rs = SLICQ_CUNIT(j.rs0 + g);
@@ -321,12 +347,15 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
 #pragma unroll
                 for (int n1 = 0; n1 < A; ++n1) v[n1] = cscale(v[n1], msrc[B * n1]);
             }
+            BINS_SET(tl_);
             dft<A, false>(v);
             y1[0] = v[0];
 #pragma unroll
-            for (int k1 = 1; k1 < A; ++k1) y1[k1 * BP] = cmul(v[k1], __ldg(tw + n2 * k1));
+            for (int k1 = 1; k1 < A; ++k1) y1[k1 * BP] = cmul(v[k1], twp[k1 * B]);
         }
+        BINS_T(t1_);
         __syncthreads();
+        BINS_T(t2_);
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
             const int slot = t / A, k1 = t - slot * A;
@@ -338,14 +367,20 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             dft<B, false>(v);
             const int off = c.y + k1;
             float2* o = p.spec + SLICQ_TROW(base + c.x) * p.spec_stride + off;
+            const float* wp = wsm + (off - coff_first);
 #pragma unroll
             for (int k2 = 0; k2 < B; ++k2) {
-                const float w = __ldg(wi + off + A * k2);
+                const float w = wp[A * k2];
                 o[A * k2] = make_float2(v[k2].x * w, v[k2].y * w);
             }
         }
+        BINS_T(t3_);
         __syncthreads();
+        BINS_T(t4_);
+        BINS_ACC(0, t0_, tl_); BINS_ACC(1, tl_, t1_); BINS_ACC(2, t1_, t2_); BINS_ACC(3, t2_, t3_); BINS_ACC(4, t3_, t4_); BINS_ACC(5, t0_, t4_);
+        BINS_COUNT();
     }
+    BINS_FLUSH(M);
 }
 
 // =========================================================================================
