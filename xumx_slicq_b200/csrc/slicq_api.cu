@@ -263,9 +263,9 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         }
         b.gt = gt;
         // + SLICQ_SLOT_BYTES; single-thread transforms keep the bucket's windows behind the stage
-        // two-pass transforms keep the job's twiddles (M complex) and dual windows (F * M floats) there too
+        // two-pass and prime transforms keep the job's twiddles (M complex) and dual windows (F * M floats) there too
         const int sm = b.n_bins * gt * b.smem_per_fft + 4096 + (f->kind == 1 ? b.n_bins * b.M * 4 + 16 : 0) +
-                       (f->kind == 2 ? b.M * 8 + b.n_bins * b.M * 4 + 16 : 0);
+                       (f->kind >= 2 ? b.M * 8 + b.n_bins * b.M * 4 + b.n_bins * 4 + 16 : 0);
         if (sm > p->bins_smem) p->bins_smem = sm;
         // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
         b.cost = (double)b.n_bins * b.M * (log2((double)b.M) + (f->kind == 3 ? 0.12 * f->A : 0.0) + 4.0);

@@ -392,9 +392,21 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
     static_assert(P * R == M, "bad split");
     constexpr int H = (P - 1) / 2;
     const int tid = threadIdx.x;
-    const float2* __restrict__ tw = p.t.tw + b.tw_off;
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float);
+    // job twiddles as [n2][k1], the bucket's analysis windows (its bins are contiguous in wf) and the
+    // spectrum offset of each bin in shared memory behind the stage
+    float2* twsm = reinterpret_cast<float2*>(sm + (size_t)j.gt * j.F * M * 2);
+    float* wsm = reinterpret_cast<float*>(twsm + M);
+    int* hoff = reinterpret_cast<int*>(wsm + j.F * M);
+    {
+        const float2* __restrict__ tw = p.t.tw + b.tw_off;
+        const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
+        for (int t = tid; t < M; t += blockDim.x) { const int c2 = t / P, k1 = t - c2 * P; twsm[t] = __ldg(tw + c2 * k1); }
+        for (int t = tid; t < j.F * M; t += blockDim.x) wsm[t] = __ldg(p.t.wf + coff_first + t);
+        for (int t = tid; t < j.F; t += blockDim.x) hoff[t] = p.t.pad_l + __ldg(p.t.bin_pos + j.first_bin + t) - M / 2;
+    }
+    __syncthreads();
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
@@ -403,13 +415,11 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             const int c = t & 1, u = t >> 1;
             const int slot = u / R, n2 = u - slot * R;
             const int gs = slot / j.F, f = slot - gs * j.F;
-            const int bin = j.first_bin + f;
-            const float* wv = p.t.wf + __ldg(p.t.bin_coff + bin) + n2;
-            const float* h = reinterpret_cast<const float*>(
-                                 p.spec + (long long)(base + gs) * p.spec_stride + p.t.pad_l + __ldg(p.t.bin_pos + bin) - M / 2 + n2) + c;
+            const float* wv = wsm + f * M + n2;
+            const float* h = reinterpret_cast<const float*>(p.spec + (long long)(base + gs) * p.spec_stride + hoff[f] + n2) + c;
             float x[P];
 #pragma unroll
-            for (int n1 = 0; n1 < P; ++n1) x[n1] = h[2 * R * n1] * __ldg(wv + R * n1);
+            for (int n1 = 0; n1 < P; ++n1) x[n1] = h[2 * R * n1] * wv[R * n1];
             rdft_sym<P>(x, sm + (size_t)(u * 2 + c) * P, 1);
         }
         __syncthreads();
@@ -431,7 +441,7 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
                     y.x -= bi;
                     y.y += br;
                 }
-                if (n2 != 0 && k1 != 0) y = cmul_conj(y, __ldg(tw + n2 * k1));
+                if (n2 != 0 && k1 != 0) y = cmul_conj(y, twsm[n2 * P + k1]);
                 v[n2] = cneg_if(y, odd);
             }
             dft<R, true>(v);
@@ -454,9 +464,19 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
     static_assert(P * R == M, "bad split");
     constexpr int H = (P - 1) / 2;
     const int tid = threadIdx.x;
-    const float2* __restrict__ tw = p.t.tw + b.tw_off;
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float);
+    // job twiddles transposed to [k1][n2] and the bucket's dual windows (its bins are contiguous in wi
+    // and in the packed row T) in shared memory behind the stage
+    float2* twsm = reinterpret_cast<float2*>(sm + (size_t)j.gt * j.F * M * 2);
+    float* wsm = reinterpret_cast<float*>(twsm + M);
+    const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
+    const int FM = j.F * M;
+    {
+        const float2* __restrict__ tw = p.t.tw + b.tw_off;
+        for (int t = tid; t < M; t += blockDim.x) { const int k1 = t / P, c2 = t - k1 * P; twsm[t] = __ldg(tw + c2 * k1); }
+        for (int t = tid; t < FM; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff_first + t);
+    }
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
@@ -478,7 +498,7 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
 #pragma unroll
             for (int k1 = 0; k1 < R; ++k1) {
                 float2 y = v[k1];
-                if (k1 != 0 && n2 != 0) y = cmul(y, __ldg(tw + n2 * k1));
+                if (k1 != 0 && n2 != 0) y = cmul(y, twsm[k1 * P + n2]);
                 float* re = sm + (size_t)((slot * R + k1) * 2) * P;
                 re[n2] = y.x;
                 re[P + n2] = y.y;
@@ -494,24 +514,29 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             rdft_sym<P>(x, row, 1);
         }
         __syncthreads();
-        // pass 2b: combine (forward direction), dual window, store
-        for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
-            const int slot = t / M, r = t - slot * M;
-            const int k2 = r / R, k1 = r - k2 * R;
-            const int gs = slot / j.F, f = slot - gs * j.F;
-            const int kk = k2 <= H ? k2 : P - k2;
-            const float* re = sm + (size_t)((slot * R + k1) * 2) * P;
-            const float* im = re + P;
-            float2 y = make_float2(re[kk], im[kk]);
-            if (k2 != 0) {
-                float br = re[P - kk], bi = im[P - kk];
-                if (k2 > H) { br = -br; bi = -bi; }   // forward: X[kk] = (Ar + Bi, Ai - Br), X[P-kk] = (Ar - Bi, Ai + Br)
-                y.x += bi;
-                y.y -= br;
+        // pass 2b: combine (forward direction), dual window, store: element e of the unit's contiguous
+        // bucket block [coff_first, coff_first + F*M); e advances by blockDim <= F*M (M >= 116 for these sizes)
+        {
+            int gs = 0, e = tid;
+            while (e >= FM) { e -= FM; ++gs; }
+            while (gs < ng) {
+                const int f = e / M, r = e - f * M;
+                const int k2 = r / R, k1 = r - k2 * R;
+                const int kk = k2 <= H ? k2 : P - k2;
+                const float* re = sm + (size_t)(((gs * j.F + f) * R + k1) * 2) * P;
+                const float* im = re + P;
+                float2 y = make_float2(re[kk], im[kk]);
+                if (k2 != 0) {
+                    float br = re[P - kk], bi = im[P - kk];
+                    if (k2 > H) { br = -br; bi = -bi; }   // forward: X[kk] = (Ar + Bi, Ai - Br), X[P-kk] = (Ar - Bi, Ai + Br)
+                    y.x += bi;
+                    y.y -= br;
+                }
+                const float wv = wsm[e];
+                p.spec[SLICQ_TROW(base + gs) * p.spec_stride + coff_first + e] = make_float2(y.x * wv, y.y * wv);
+                e += blockDim.x;
+                while (e >= FM) { e -= FM; ++gs; }
             }
-            const int coff = __ldg(p.t.bin_coff + j.first_bin + f) + r;
-            const float wv = __ldg(p.t.wi + coff);
-            p.spec[SLICQ_TROW(base + gs) * p.spec_stride + coff] = make_float2(y.x * wv, y.y * wv);
         }
         __syncthreads();
     }
