@@ -104,6 +104,15 @@ def test_wrappers_layout_and_shapes(base, orc, golden_dir):
     Xp = [t.permute(0, 1, 3, 2, 4, 5).contiguous().permute(0, 1, 3, 2, 4, 5) for t in X]
     assert not Xp[1].is_contiguous()
     np.testing.assert_allclose(insgt(Xp, x.shape[-1]).numpy(), y.numpy(), atol=1e-7)
+    # buckets whose storage starts on an odd complex element (8- but not 16-byte aligned): the kernels
+    # fall back from their 16-byte loads; same values, bit for bit
+    Xo = []
+    for t in X:
+        flat = torch.empty(t.numel() + 2, dtype=torch.float32)
+        flat[2:].copy_(t.reshape(-1))
+        Xo.append(flat[2:].view(t.shape))
+    assert Xo[1].data_ptr() % 16 == 8 or X[1].data_ptr() % 16 == 8
+    assert torch.equal(insgt(Xo, x.shape[-1]), y)
 
 
 def test_edge_lengths(base, golden_dir):

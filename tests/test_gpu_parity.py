@@ -129,6 +129,15 @@ def test_wrappers_dropin_contract(base, dev, orc, golden_dir):
     assert X4[1].dim() == 7 and X4[1].shape[:3] == (4, 1, 2)
     # float64 input -> float32 output
     assert nsgt(x.double())[0].dtype == torch.float32
+    # buckets starting on an odd complex element (8- but not 16-byte aligned storage): the 16-byte load paths
+    # fall back; same values bit for bit
+    Xo = []
+    for t in X:
+        flat = torch.empty(t.numel() + 2, dtype=torch.float32, device=dev)
+        flat[2:].copy_(t.reshape(-1))
+        Xo.append(flat[2:].view(t.shape))
+    assert Xo[1].data_ptr() % 16 == 8
+    assert torch.equal(insgt(Xo, x.shape[-1]), y)
     # deepcopy / .to() plumbing (training.py:118,356)
     b2 = copy.deepcopy(base).to(dev)
     X2 = make_filterbanks(b2)[0](x)
