@@ -366,7 +366,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     if (mb < 1) mb = 1;
     p->chunk_bytes = mb << 20;
     const char* envj = getenv("SLICQ_BINS_JOBS");
-    p->target_jobs = envj ? atoi(envj) : 1184;   // 148 SMs x 2-4 resident CTAs x 2-4 waves
+    p->target_jobs = envj ? atoi(envj) : 2220;   // 148 SMs x 3 resident CTAs x 5 waves: short jobs even out the tail (swept 666 ... 8880)
     if (p->target_jobs < 1) p->target_jobs = 1;
     const char* envs = getenv("SLICQ_SPLIT_UNITS");
     p->split_units = envs ? atoll(envs) : 1184;
