@@ -461,6 +461,45 @@ def main():
         single = {"mixtures_per_step": 1, "ms_per_step": ms1, "value": SECONDS / (ms1 * 1e-3), "unit": "audio-s/s",
                   "roofline_frac": round(B_UNIT * (2 + 2 * N_TARGETS) * S / (ms1 * 1e-3) / 1e9 / peak, 4)}
 
+    # ---- the fused variant of the same step: forward that also writes |X|, inverse that
+    #      reads the mixture coefficients + 4 fp32 masks instead of 4 materialised target coefficient sets
+    fused = None
+    if world == 1:
+        del Y
+        torch.cuda.empty_cache()
+        nslab, Nout = nsg.alloc_norms(rows_f, S, dev)
+        masks = [torch.full((rows_i,) + tuple(c.shape[1:]), 1.0, device=dev) for c in Cout]
+        for m in masks:                              # mask of target t = its gain: same waveforms as the plain step
+            for t_, g_ in enumerate(GAINS):
+                m[t_ * rows_f:(t_ + 1) * rows_f] = g_
+        views_m = [(m.data_ptr(), m.stride(0), m.stride(1), m.stride(2)) for m in masks]
+        sbm = plan.scratch_bytes(rows_i, S, True)
+        scr_m = scratch if sbm <= scratch.numel() else torch.empty(sbm, dtype=torch.uint8, device=dev)
+
+        def step_fused():
+            plan.forward_packed_norm(x.data_ptr(), rows_f, x.stride(0), T, 0, 0, S, slab.data_ptr(), nslab.data_ptr(),
+                                     scr_m.data_ptr(), sb_f, stream.cuda_stream)
+            plan.inverse_masked(views_f, views_m, N_TARGETS, rows_f, S, 0, yout.data_ptr(), yout.stride(0), T, 0, 0,
+                                scr_m.data_ptr(), sbm, stream.cuda_stream)
+        for _ in range(3):
+            step_fused()
+        torch.cuda.synchronize(dev)
+        nfu = 20
+        evf = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nfu)]
+        for a, b in evf:
+            flush.fill_(1)
+            a.record(stream); step_fused(); b.record(stream)
+        torch.cuda.synchronize(dev)
+        msf = float(np.mean([a.elapsed_time(b) for a, b in evf]))
+        ferr = float((yout[:rows_f] - GAINS[0] * x).abs().max())
+        # algorithmic bytes of the fused step: fwd 185 240 + 4 * 18 640 (|X|), inverse 18 640 * (8 + 4*4) + 4 * 36 120
+        fb = (B_UNIT + 4 * 18640) * units_f + (18640 * (8 + 4 * N_TARGETS) + N_TARGETS * B_IN) * units_f
+        fused = {"ms_per_step": msf, "value": audio_s / (msf * 1e-3), "unit": "audio-s/s",
+                 "what": "forward_with_norm (coefficients + |X|) + inverse_masked (mixture + 4 fp32 masks -> 4 target waveforms)",
+                 "algorithmic_bytes_per_step": int(fb), "roofline_frac": round(fb / (msf * 1e-3) / 1e9 / peak, 4),
+                 "max_abs_err_target0": ferr}
+        del masks, nslab
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores, sample = cpu_reference_arm(3, 1, args.cpu_sample_seconds)
@@ -472,7 +511,7 @@ def main():
             "metric": "sliCQT fwd+inv audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_mixture": single,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_mixture": single, "fused_step": fused,
             "gpu_launches": int(launches),
             "clocks": clocks, "max_abs_err_target0": err,
         }))

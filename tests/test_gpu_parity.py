@@ -268,6 +268,13 @@ def test_masked_inverse_fused(base, dev):
     y = insgt.forward_masked(X, masks, x.shape[-1])
     assert y.shape == (4, 2, 2, x.shape[-1])
     assert torch.equal(y, y_ref)
+    # large call: the library splits the output rows over its two internal streams (row groups start on a
+    # multiple of the mixture rows)
+    x = torch.rand(4, 2, 700000, device=dev) * 2 - 1
+    X = nsgt(x)
+    masks = [torch.rand((4,) + tuple(Xb.shape[:-1]), device=dev) for Xb in X]
+    y_ref = insgt([m.unsqueeze(-1) * Xb.unsqueeze(0) for m, Xb in zip(masks, X)], x.shape[-1])
+    assert torch.equal(insgt.forward_masked(X, masks, x.shape[-1]), y_ref)
 
 
 def test_forward_with_norm_fused(base, dev):

@@ -366,8 +366,11 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     if (mb < 1) mb = 1;
     p->chunk_bytes = mb << 20;
     const char* envj = getenv("SLICQ_BINS_JOBS");
-    p->target_jobs = envj ? atoi(envj) : 2220;   // 148 SMs x 3 resident CTAs x 5 waves: short jobs even out the tail (swept 666 ... 8880)
-    if (p->target_jobs < 1) p->target_jobs = 1;
+    // jobs per bins launch: 148 SMs x 3 resident CTAs x 5 waves for large launches (short jobs even out the tail;
+    // swept 666 ... 8880 at batch 8), 1184 for small ones (a job keeps enough iterations to amortise its set-up);
+    // SLICQ_BINS_JOBS fixes the number
+    p->target_jobs = envj ? atoi(envj) : 0;
+    if (p->target_jobs < 0) p->target_jobs = 0;
     const char* envs = getenv("SLICQ_SPLIT_UNITS");
     p->split_units = envs ? atoll(envs) : 1184;
     const char* envw = getenv("SLICQ_SPLIT_WAYS");
@@ -456,6 +459,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
     bp.n_buckets = (int)p->buckets.size();
     double total = 0.0;
     for (const Bucket& b : p->buckets) total += b.cost;
+    const int target = p->target_jobs > 0 ? p->target_jobs : std::min(2220, std::max(1184, n_rs / 2));
     for (size_t i = 0; i < p->buckets.size(); ++i) {
         const Bucket& b = p->buckets[i];
         SlicqBucketArg& a = bp.b[i];
@@ -471,7 +475,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
             continue;
         }
         const int groups = (n_rs + b.gt - 1) / b.gt;                 // iterations available in this chunk
-        int nj = (int)(p->target_jobs * b.cost / total + 0.5);
+        int nj = (int)(target * b.cost / total + 0.5);
         if (nj > groups / p->min_iters) nj = groups / p->min_iters;
         if (nj < 1) nj = 1;
         const int gpj = (groups + nj - 1) / nj;                      // iterations per job
@@ -640,12 +644,23 @@ int inverse_impl(const slicq_plan* p, const slicq_bucket_view* buckets, const sl
     for (size_t i = 0; i < p->buckets.size(); ++i)
         if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
     cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
-    if (!masks && use_split(p, n_rows, n_slices)) {
+    // masked synthesis: output row r reads mixture row r % x_rows, so a row group must start on a multiple of x_rows
+    bool split = use_split(p, n_rows, n_slices);
+    if (split && masks) {
+        const int ways = split_ways(p, n_rows);
+        for (int h = 1; h < ways; ++h) split = split && (part_row0(n_rows, ways, h) % x_rows == 0);
+    }
+    if (split) {
         return run_split(p, n_rows, n_slices, 1, scratch, s0, [&](int64_t r0, int64_t rows, void* scr, cudaStream_t st) {
-            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size());
-            for (auto& b : v) b.ptr = reinterpret_cast<float2*>(b.ptr) + r0 * b.s_row;
-            return inverse_one(p, v.data(), nullptr, 0, rows, n_slices, k0, y + r0 * y_row_stride, y_row_stride, length, t0,
-                               halo_out ? halo_out + r0 * p->hop : nullptr, scr, st);
+            std::vector<slicq_bucket_view> v(buckets, buckets + p->buckets.size()), mv;
+            if (masks) {        // the mixture is shared by all row groups, the masks follow the output rows
+                mv.assign(masks, masks + p->buckets.size());
+                for (auto& b : mv) b.ptr = reinterpret_cast<float*>(b.ptr) + r0 * b.s_row;
+            } else {
+                for (auto& b : v) b.ptr = reinterpret_cast<float2*>(b.ptr) + r0 * b.s_row;
+            }
+            return inverse_one(p, v.data(), masks ? mv.data() : nullptr, x_rows, rows, n_slices, k0, y + r0 * y_row_stride,
+                               y_row_stride, length, t0, halo_out ? halo_out + r0 * p->hop : nullptr, scr, st);
         });
     }
     return inverse_one(p, buckets, masks, x_rows, n_rows, n_slices, k0, y, y_row_stride, length, t0, halo_out, scratch, s0);
