@@ -172,7 +172,7 @@ def bench_slices(args, nsg, dev, rank, world, distributed):
     ms = float(t.item())
     err = float((y[:2] - gains[0] * x_local).abs().max())
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "sliCQT fwd+inv audio-sec/sec", "value": 180.0 / (ms * 1e-3), "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -186,7 +186,30 @@ def bench_slices(args, nsg, dev, rank, world, distributed):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout() -> None:
+    """stdout carries exactly ONE JSON line: everything else a library prints to file descriptor 1 (the NCCL
+    version banner, build chatter) is redirected to stderr; emit() writes to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -219,7 +242,7 @@ def main():
         cores = os.cpu_count() or 1
         steps = max(1, min(args.steps, 5))
         val, dt, cores, sample = cpu_reference_arm(steps, min(args.warmup, 1), args.cpu_sample_seconds)
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "sliCQT fwd+inv audio-sec/sec", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -507,7 +530,7 @@ def main():
                "ms_per_sample": dt * 1e3}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "sliCQT fwd+inv audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
