@@ -42,6 +42,12 @@ def _worker(rank, world, port, T, out_dir):
         assert (sh.k0, sh.k1) == slice_partition(nsg.n_slices(T), world)[rank]
         C = sh.forward(sh.local_input(x))
         y = sh.inverse(C)
+        # fused mask * mixture on the shard: two targets with constant masks == scaled plain synthesis of the shard
+        masks = [torch.stack([torch.full(tuple(c.shape), g, dtype=torch.float32) for g in (0.75, 0.25)]) for c in C]
+        ym = sh.inverse_masked(C, masks)
+        y2 = sh.inverse([torch.cat([c * 0.75, c * 0.25], dim=0) for c in C])
+        assert ym.shape == y2.shape == (4, sh.hi - sh.lo)
+        assert torch.equal(ym, y2), "sharded masked synthesis differs from the plain one"
         torch.save({"k0": sh.k0, "k1": sh.k1, "lo": sh.lo, "hi": sh.hi, "C": C, "y": y},
                    os.path.join(out_dir, f"rank{rank}.pt"))
         dist.barrier()

@@ -102,13 +102,25 @@ class SliceShardedSliCQT:
     # -- synthesis ------------------------------------------------------------------------
     def inverse(self, coefs: Sequence[torch.Tensor]) -> torch.Tensor:
         """coefficient buckets of slices [k0, k1) -> this rank's owned samples [rows, hi-lo]."""
-        rows = coefs[0].shape[0]
+        return self._inverse(coefs[0].shape[0], coefs[0].device,
+                             lambda halo_out: self.nsgt.backward_rows(coefs, self.hi - self.lo, k0=self.k0,
+                                                                      t0=self.k0 * self.hop, halo_out=halo_out))
+
+    def inverse_masked(self, mix: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Sharded synthesis fused with mask * mixture (``NSGT_sliced.backward_rows_masked``): mix buckets
+        [rows, F_b, k1-k0, M_b] of this rank's slices, masks [targets, rows, F_b, k1-k0, M_b] -> owned samples
+        [targets * rows, hi-lo]; the halo exchange is the same single message per boundary."""
+        rows = masks[0].shape[0] * mix[0].shape[0]
+        return self._inverse(rows, mix[0].device,
+                             lambda halo_out: self.nsgt.backward_rows_masked(mix, masks, self.hi - self.lo, k0=self.k0,
+                                                                             t0=self.k0 * self.hop, halo_out=halo_out))
+
+    def _inverse(self, rows: int, dev, synth) -> torch.Tensor:
         hop = self.hop
-        dev = coefs[0].device
         left = self.rank - 1 if self.rank > 0 else None
         right = self.rank + 1 if self.rank + 1 < self.world else None
         halo_out = torch.zeros(rows, hop, dtype=torch.float32, device=dev) if left is not None else None
-        y = self.nsgt.backward_rows(coefs, self.hi - self.lo, k0=self.k0, t0=self.k0 * hop, halo_out=halo_out)
+        y = synth(halo_out)
         halo_in = torch.empty(rows, hop, dtype=torch.float32, device=dev) if right is not None else None
         self._exchange(left, halo_out, right, halo_in)
         if right is not None:
