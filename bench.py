@@ -489,6 +489,26 @@ def main():
         ms1 = float(np.mean([a.elapsed_time(b) for a, b in ev1]))
         single = {"mixtures_per_step": 1, "ms_per_step": ms1, "value": SECONDS / (ms1 * 1e-3), "unit": "audio-s/s",
                   "roofline_frac": round(B_UNIT * (2 + 2 * N_TARGETS) * S / (ms1 * 1e-3) / 1e9 / peak, 4)}
+        # the same step captured once into a CUDA graph (kernels + the fork/join of the two internal streams) and replayed
+        try:
+            gs = torch.cuda.Stream(device=dev)
+            gs.wait_stream(stream)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=gs):
+                cs = torch.cuda.current_stream(dev).cuda_stream
+                plan.forward(x1.data_ptr(), 2, x1.stride(0), T, 0, 0, S, vf1, scratch.data_ptr(), s1f, cs)
+                plan.inverse(vi1, 2 * N_TARGETS, S, 0, y1.data_ptr(), y1.stride(0), T, 0, 0, scratch.data_ptr(), s1i, cs)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            evg = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n1)]
+            for a, b in evg:
+                flush.fill_(1)
+                a.record(stream); graph.replay(); b.record(stream)
+            torch.cuda.synchronize(dev)
+            single["graph_ms_per_step"] = float(np.mean([a.elapsed_time(b) for a, b in evg]))
+        except Exception as e:                      # informational only
+            single["graph_error"] = str(e)[:200]
 
     # ---- the fused variant of the same step: forward that also writes |X|, inverse that
     #      reads the mixture coefficients + 4 fp32 masks instead of 4 materialised target coefficient sets

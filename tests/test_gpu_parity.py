@@ -314,3 +314,34 @@ def test_inverse_autograd_adjoint(base, dev):
         C2 = [c - 200.0 * c.grad for c in C]
         loss1 = ((insgt(C2, T) - target) ** 2).mean()
     assert float(loss1) < float(loss0)
+
+
+def test_cuda_graph_capture_of_the_path(base, dev):
+    """The library only launches kernels and forks / joins its two internal streams with events, so a whole
+    forward + inverse (wrappers included) can be captured into a CUDA graph and replayed on new input."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    T = 400000
+    x_static = torch.rand(8, 2, T, device=dev) * 2 - 1        # 16 rows x 46 slices: forward unsplit, 64-row inverse split
+    def step():
+        X = nsgt(x_static)
+        return insgt([torch.stack([Xb * g for g in (0.9, 0.6, 0.4, 0.2)]) for Xb in X], T)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()                                              # warm-up: plan, side streams, allocator
+    torch.cuda.current_stream(dev).wait_stream(s)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        y_static = step()
+    x_new = torch.rand(8, 2, T, device=dev) * 2 - 1
+    x_static.copy_(x_new)
+    g.replay()
+    torch.cuda.synchronize(dev)
+    y_graph = y_static.clone()
+    y_eager = step()
+    assert torch.equal(y_graph, y_eager)
+    assert float((y_graph[0] - 0.9 * x_new).abs().max()) < 1e-5
+
