@@ -271,8 +271,9 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
 // stage 3b + 4: one CTA per (row, slice).  packed windowed bin spectra T -> slice signal u[L],
 // overlap-added straight into y:  y[(k-1)*hop + p] += u_k[p].  Every output sample is the sum of
 // exactly two slices, one even and one odd: the launch with parity 0 STORES the even slices, the
-// launch with parity 1 (stream-ordered after it) ACCUMULATES the odd ones -- no atomics, no
-// intermediate slice buffer, and a two-term sum is order independent (bitwise reproducible).
+// launch with parity 1 (stream-ordered after it) ADDS the odd ones with fire-and-forget reductions
+// (red.global.add: every location receives exactly one addition, so no ordering question arises) --
+// no intermediate slice buffer, and a two-term sum is order independent (bitwise reproducible).
 // (reference: nsgt/unslicing.py:33-69, nsgt/slicq.py:207-230)
 template <class PF>
 __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
