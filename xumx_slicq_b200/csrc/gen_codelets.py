@@ -6,8 +6,11 @@
 
 Two families are emitted into ``dft_codelets.cuh``:
 
-* ``dft<N, INV>(float2 (&v)[N])``   in-place complex DFT of compile-time size N with
-  natural-order output.  Built recursively: Good-Thomas prime-factor split where
+* ``dft<N, INV>(cpx (&v)[N])``   in-place complex DFT of compile-time size N with
+  natural-order output, written in PACKED complex operations (slicq_cpx.cuh: one FADD2 / FMUL2 /
+  FFMA2 per complex add, real scaling or multiply-accumulate; multiplications by +-i and negations
+  are carried as lazy tags and folded into the consuming operation's lane modifiers).
+  Built recursively: Good-Thomas prime-factor split where
   the factors are coprime (no twiddles), Cooley-Tukey with constant twiddles
   inside prime powers, radix-2/4 butterflies, and -- for odd primes -- the
   symmetric direct form  X[k], X[p-k] = x0 + sum a_n cos(.) -/+ i sum b_n sin(.)
@@ -77,7 +80,7 @@ def factorize(n: int) -> Dict[int, int]:
 
 
 class Emitter:
-    """Tiny SSA builder; values are variable names (strings) or numeric evaluation."""
+    """Scalar SSA builder (real values) used by the real symmetric half transforms."""
 
     def __init__(self):
         self.ops: List[Tuple[str, str, tuple]] = []  # (dst, op, args)
@@ -94,14 +97,7 @@ class Emitter:
     def sub(self, a, b):
         d = self._new(); self.ops.append((d, "sub", (a, b))); self.flops += 1; return d
 
-    def neg(self, a):
-        d = self._new(); self.ops.append((d, "neg", (a,))); return d
-
     def mulc(self, a, c: float):
-        if c == 1.0:
-            return a
-        if c == -1.0:
-            return self.neg(a)
         d = self._new(); self.ops.append((d, "mulc", (a, c))); self.flops += 1; return d
 
     def fmac(self, a, c: float, acc):
@@ -110,17 +106,6 @@ class Emitter:
             return acc
         d = self._new(); self.ops.append((d, "fmac", (a, c, acc))); self.flops += 1; return d
 
-    # ---- rendering -------------------------------------------------------
-    @staticmethod
-    def _lit(c: float) -> str:
-        s = repr(float.fromhex(float(c).hex()))
-        import struct
-        f32 = struct.unpack("f", struct.pack("f", c))[0]
-        s = f"{f32:.9g}"
-        if "e" not in s and "." not in s:
-            s += ".0"
-        return s + "f"
-
     def render(self, indent="    ") -> List[str]:
         out = []
         for d, op, a in self.ops:
@@ -128,103 +113,188 @@ class Emitter:
                 out.append(f"{indent}const float {d} = {a[0]} + {a[1]};")
             elif op == "sub":
                 out.append(f"{indent}const float {d} = {a[0]} - {a[1]};")
-            elif op == "neg":
-                out.append(f"{indent}const float {d} = -{a[0]};")
             elif op == "mulc":
-                out.append(f"{indent}const float {d} = {a[0]} * {self._lit(a[1])};")
+                out.append(f"{indent}const float {d} = {a[0]} * {lit(a[1])};")
             elif op == "fmac":
-                out.append(f"{indent}const float {d} = fmaf({a[0]}, {self._lit(a[1])}, {a[2]});")
+                out.append(f"{indent}const float {d} = fmaf({a[0]}, {lit(a[1])}, {a[2]});")
         return out
 
-    def evaluate(self, env: Dict[str, float]) -> Dict[str, float]:
+
+def _scalar_evaluate(e: "Emitter", env: Dict[str, float]) -> Dict[str, float]:
+    import numpy as np
+    f = np.float32
+    for d, op, a in e.ops:
+        if op == "add":
+            env[d] = f(env[a[0]] + env[a[1]])
+        elif op == "sub":
+            env[d] = f(env[a[0]] - env[a[1]])
+        elif op == "mulc":
+            env[d] = f(env[a[0]] * f(a[1]))
+        elif op == "fmac":
+            env[d] = f(np.float64(env[a[0]]) * np.float64(f(a[1])) + np.float64(env[a[2]]))
+    return env
+
+
+def lit(c: float) -> str:
+    import struct
+    f32 = struct.unpack("f", struct.pack("f", c))[0]
+    s = f"{f32:.9g}"
+    if "e" not in s and "." not in s and "inf" not in s and "nan" not in s:
+        s += ".0"
+    return s + "f"
+
+
+class CV:
+    """A complex SSA value times i^rot (lazy multiplication by +-1, +-i)."""
+    __slots__ = ("name", "rot")
+
+    def __init__(self, name: str, rot: int = 0):
+        self.name = name
+        self.rot = rot & 3
+
+    def times_i(self, k: int = 1) -> "CV":
+        return CV(self.name, self.rot + k)
+
+
+class CEmitter:
+    """Complex SSA builder: every op is one packed instruction (slicq_cpx.cuh)."""
+
+    def __init__(self):
+        self.ops: List[Tuple[str, str, tuple]] = []
+        self.cnt = 0
+        self.flops = 0     # packed instructions
+
+    def _emit(self, op: str, args: tuple) -> str:
+        self.cnt += 1
+        d = f"t{self.cnt}"
+        self.ops.append((d, op, args))
+        self.flops += 1
+        return d
+
+    def add(self, a: CV, b: CV) -> CV:
+        op = ("cadd", "caddi", "csub", "csubi")[(b.rot - a.rot) & 3]
+        return CV(self._emit(op, (a.name, b.name)), a.rot)
+
+    def sub(self, a: CV, b: CV) -> CV:
+        return self.add(a, b.times_i(2))
+
+    def mulr(self, a: CV, c: float) -> CV:
+        if c == 1.0:
+            return a
+        if c == -1.0:
+            return a.times_i(2)
+        return CV(self._emit("cmulr", (a.name, c)), a.rot)
+
+    def fmar(self, a: CV, c: float, acc: CV) -> CV:
+        """acc + c * a"""
+        if c == 0.0:
+            return acc
+        d = (a.rot - acc.rot) & 3
+        if d == 0:
+            return CV(self._emit("cfmar", (a.name, c, acc.name)), acc.rot)
+        if d == 2:
+            return CV(self._emit("cfmar", (a.name, -c, acc.name)), acc.rot)
+        if d == 1:
+            return CV(self._emit("cfmai", (a.name, c, acc.name)), acc.rot)
+        return CV(self._emit("cfmai", (a.name, -c, acc.name)), acc.rot)
+
+    def mulw(self, a: CV, c: float, s: float) -> CV:
+        """a * (c + i s)"""
+        if s == 0.0:
+            return self.mulr(a, c)
+        if c == 0.0:
+            return self.mulr(a.times_i(1), s)
+        t = self._emit("cmulr", (a.name, c))
+        return CV(self._emit("cfmai", (a.name, s, t)), a.rot)
+
+    def plain(self, a: CV) -> str:
+        """materialise the lazy rotation"""
+        if a.rot == 0:
+            return a.name
+        if a.rot == 2:
+            return self._emit("cmulr", (a.name, -1.0))
+        return self._emit("cmulir", (a.name, 1.0 if a.rot == 1 else -1.0))
+
+    def render(self, indent="    ") -> List[str]:
+        out = []
+        for d, op, a in self.ops:
+            if op in ("cadd", "csub", "caddi", "csubi"):
+                out.append(f"{indent}const cpx {d} = {op}({a[0]}, {a[1]});")
+            elif op in ("cmulr", "cmulir"):
+                out.append(f"{indent}const cpx {d} = {op}({a[0]}, {lit(a[1])});")
+            else:
+                out.append(f"{indent}const cpx {d} = {op}({a[0]}, {lit(a[1])}, {a[2]});")
+        return out
+
+    def evaluate(self, env: Dict[str, complex]) -> Dict[str, complex]:
+        """float32 model of the packed operations (fma = one rounding)"""
         import numpy as np
         f = np.float32
+
+        def c32(re, im):
+            return complex(f(re), f(im))
+
+        def fma(x, y, z):
+            return f(np.float64(x) * np.float64(y) + np.float64(z))
+
         for d, op, a in self.ops:
-            if op == "add":
-                env[d] = f(env[a[0]] + env[a[1]])
-            elif op == "sub":
-                env[d] = f(env[a[0]] - env[a[1]])
-            elif op == "neg":
-                env[d] = f(-env[a[0]])
-            elif op == "mulc":
-                env[d] = f(env[a[0]] * f(a[1]))
-            elif op == "fmac":
-                env[d] = f(np.float64(env[a[0]]) * np.float64(f(a[1])) + np.float64(env[a[2]]))
+            x = env[a[0]]
+            if op == "cadd":
+                y = env[a[1]]; env[d] = c32(f(x.real) + f(y.real), f(x.imag) + f(y.imag))
+            elif op == "csub":
+                y = env[a[1]]; env[d] = c32(f(x.real) - f(y.real), f(x.imag) - f(y.imag))
+            elif op == "caddi":
+                y = env[a[1]]; env[d] = c32(f(x.real) - f(y.imag), f(x.imag) + f(y.real))
+            elif op == "csubi":
+                y = env[a[1]]; env[d] = c32(f(x.real) + f(y.imag), f(x.imag) - f(y.real))
+            elif op == "cmulr":
+                env[d] = c32(f(x.real) * f(a[1]), f(x.imag) * f(a[1]))
+            elif op == "cmulir":
+                env[d] = c32(-f(x.imag) * f(a[1]), f(x.real) * f(a[1]))
+            elif op == "cfmar":
+                z = env[a[2]]; env[d] = c32(fma(x.real, f(a[1]), z.real), fma(x.imag, f(a[1]), z.imag))
+            elif op == "cfmai":
+                z = env[a[2]]; env[d] = c32(fma(-f(x.imag), f(a[1]), z.real), fma(x.real, f(a[1]), z.imag))
         return env
 
 
-C = Tuple[str, str]  # complex value = (re name, im name)
-
-
-def cadd(e: Emitter, a: C, b: C) -> C:
-    return (e.add(a[0], b[0]), e.add(a[1], b[1]))
-
-
-def csub(e: Emitter, a: C, b: C) -> C:
-    return (e.sub(a[0], b[0]), e.sub(a[1], b[1]))
-
-
-def cmul_const(e: Emitter, a: C, c: float, s: float) -> C:
-    """a * (c + i s)"""
-    if s == 0.0:
-        return (e.mulc(a[0], c), e.mulc(a[1], c))
-    if c == 0.0:
-        # a * (i s) = (-a.im*s, a.re*s)
-        return (e.mulc(a[1], -s), e.mulc(a[0], s))
-    re = e.fmac(a[1], -s, e.mulc(a[0], c))
-    im = e.fmac(a[1], c, e.mulc(a[0], s))
-    return (re, im)
-
-
-def mul_i(e: Emitter, a: C, sign: int) -> C:
-    """a * (sign * i)"""
-    if sign > 0:
-        return (e.neg(a[1]), a[0])
-    return (a[1], e.neg(a[0]))
-
-
-def dft_prime_sym(e: Emitter, x: List[C], sign: int) -> List[C]:
+def dft_prime_sym(e: CEmitter, x: List[CV], sign: int) -> List[CV]:
     p = len(x)
     h = (p - 1) // 2
-    a = [None] + [cadd(e, x[n], x[p - n]) for n in range(1, h + 1)]
-    b = [None] + [csub(e, x[n], x[p - n]) for n in range(1, h + 1)]
-    out: List[C] = [None] * p
-    sr, si = x[0]
+    a = [None] + [e.add(x[n], x[p - n]) for n in range(1, h + 1)]
+    b = [None] + [e.sub(x[n], x[p - n]) for n in range(1, h + 1)]
+    out: List[CV] = [None] * p
+    s = x[0]
     for n in range(1, h + 1):
-        sr = e.add(sr, a[n][0]); si = e.add(si, a[n][1])
-    out[0] = (sr, si)
+        s = e.add(s, a[n])
+    out[0] = s
     for k in range(1, h + 1):
-        ar, ai = x[0]
-        br = bi = None
+        A = x[0]
+        B = None
         for n in range(1, h + 1):
-            c = cospi2(n * k, p)
-            s = sinpi2(n * k, p)
-            ar = e.fmac(a[n][0], c, ar)
-            ai = e.fmac(a[n][1], c, ai)
-            br = e.mulc(b[n][0], s) if br is None else e.fmac(b[n][0], s, br)
-            bi = e.mulc(b[n][1], s) if bi is None else e.fmac(b[n][1], s, bi)
-        # forward (sign=-1): X[k] = A - iB ; X[p-k] = A + iB  (B complex)
+            A = e.fmar(a[n], cospi2(n * k, p), A)
+            sv = sinpi2(n * k, p)
+            B = e.mulr(b[n], sv) if B is None else e.fmar(b[n], sv, B)
+        # forward (sign=-1): X[k] = A - iB ; X[p-k] = A + iB
         if sign < 0:
-            out[k] = (e.add(ar, bi), e.sub(ai, br))
-            out[p - k] = (e.sub(ar, bi), e.add(ai, br))
+            out[k] = e.add(A, B.times_i(3)); out[p - k] = e.add(A, B.times_i(1))
         else:
-            out[k] = (e.sub(ar, bi), e.add(ai, br))
-            out[p - k] = (e.add(ar, bi), e.sub(ai, br))
+            out[k] = e.add(A, B.times_i(1)); out[p - k] = e.add(A, B.times_i(3))
     return out
 
 
-def dft(e: Emitter, x: List[C], sign: int) -> List[C]:
+def dft(e: CEmitter, x: List[CV], sign: int) -> List[CV]:
     """DFT of the list x with kernel exp(sign*2*pi*i*n*k/N); natural order in and out."""
     n = len(x)
     if n == 1:
         return list(x)
     if n == 2:
-        return [cadd(e, x[0], x[1]), csub(e, x[0], x[1])]
+        return [e.add(x[0], x[1]), e.sub(x[0], x[1])]
     if n == 4:
-        s02 = cadd(e, x[0], x[2]); d02 = csub(e, x[0], x[2])
-        s13 = cadd(e, x[1], x[3]); d13 = csub(e, x[1], x[3])
-        jd = mul_i(e, d13, sign)  # sign*i*(x1-x3)
-        return [cadd(e, s02, s13), cadd(e, d02, jd), csub(e, s02, s13), csub(e, d02, jd)]
+        s02 = e.add(x[0], x[2]); d02 = e.sub(x[0], x[2])
+        s13 = e.add(x[1], x[3]); d13 = e.sub(x[1], x[3])
+        jd = d13.times_i(1 if sign > 0 else 3)  # sign*i*(x1-x3)
+        return [e.add(s02, s13), e.add(d02, jd), e.sub(s02, s13), e.sub(d02, jd)]
     fac = factorize(n)
     if len(fac) == 1 and list(fac.values())[0] == 1:
         return dft_prime_sym(e, x, sign)
@@ -233,11 +303,10 @@ def dft(e: Emitter, x: List[C], sign: int) -> List[C]:
         p = max(fac, key=lambda q: q ** fac[q])  # largest prime-power first
         n1 = p ** fac[p]
         n2 = n // n1
-        # input (Ruritanian): x2[a][b] = x[(a*n2 + b*n1) % n]
         inner = []
         for b in range(n2):
             inner.append(dft(e, [x[(a * n2 + b * n1) % n] for a in range(n1)], sign))
-        out: List[C] = [None] * n
+        out: List[CV] = [None] * n
         i1 = pow(n2, -1, n1)
         i2 = pow(n1, -1, n2)
         for k1 in range(n1):
@@ -261,7 +330,7 @@ def dft(e: Emitter, x: List[C], sign: int) -> List[C]:
         for b in range(n2):
             v = inner[b][k1]
             if b * k1 != 0:
-                v = cmul_const(e, v, cospi2(b * k1, n), sign * sinpi2(b * k1, n))
+                v = e.mulw(v, cospi2(b * k1, n), sign * sinpi2(b * k1, n))
             col_in.append(v)
         col = dft(e, col_in, sign)
         for k2 in range(n2):
@@ -270,15 +339,13 @@ def dft(e: Emitter, x: List[C], sign: int) -> List[C]:
 
 
 def gen_complex(n: int, inv: bool) -> Tuple[List[str], int]:
-    e = Emitter()
-    x = [(f"v[{i}].x", f"v[{i}].y") for i in range(n)]
-    # read inputs into named scalars first so that in-place writes are safe
-    pre = [f"    const float xr{i} = v[{i}].x, xi{i} = v[{i}].y;" for i in range(n)]
-    x = [(f"xr{i}", f"xi{i}") for i in range(n)]
-    y = dft(e, x, +1 if inv else -1)
+    e = CEmitter()
+    pre = [f"    const cpx x{i} = v[{i}];" for i in range(n)]
+    y = dft(e, [CV(f"x{i}") for i in range(n)], +1 if inv else -1)
+    outs = [e.plain(v) for v in y]
     body = pre + e.render()
     for i in range(n):
-        body.append(f"    v[{i}] = make_float2({y[i][0]}, {y[i][1]});")
+        body.append(f"    v[{i}] = {outs[i]};")
     return body, e.flops
 
 
@@ -323,19 +390,26 @@ def gen_real_sym(p: int) -> Tuple[List[str], int]:
 HEADER = '''// GENERATED by gen_codelets.py -- do not edit by hand.
 // Register-resident DFT codelets for the sliCQT kernels (see gen_codelets.py docstring).
 #pragma once
+#include "slicq_cpx.cuh"
 
-#ifndef SLICQ_DEVFN
-#define SLICQ_DEVFN __device__ __forceinline__
-#endif
-
-// dft<N, INV>(v): in-place complex DFT, kernel exp(-/+ 2 pi i nk/N), natural order, unnormalised.
-template <int N, bool INV> SLICQ_DEVFN void dft(float2 (&v)[N]);
+// dft<N, INV>(v): in-place complex DFT, kernel exp(-/+ 2 pi i nk/N), natural order, unnormalised;
+// packed complex arithmetic (one FADD2 / FMUL2 / FFMA2 per operation).
+template <int N, bool INV> SLICQ_DEVFN void dft(cpx (&v)[N]);
+// the same on float2 registers (conversions are register renames)
+template <int N, bool INV> SLICQ_DEVFN void dft(float2 (&v)[N]) {
+    cpx c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = cpx_from(v[i]);
+    dft<N, INV>(c);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = cpx_to(c[i]);
+}
 // rdft_sym<P>(x, out, stride): real symmetric half-transform for odd prime P:
 //   out[0] = sum_n x[n];  out[k*stride] = x0 + sum a_n cos(2 pi nk/P);  out[(P-k)*stride] = sum b_n sin(2 pi nk/P)
 template <int P> SLICQ_DEVFN void rdft_sym(const float (&x)[P], float* out, int stride);
 
-template <> SLICQ_DEVFN void dft<1, false>(float2 (&)[1]) {}
-template <> SLICQ_DEVFN void dft<1, true>(float2 (&)[1]) {}
+template <> SLICQ_DEVFN void dft<1, false>(cpx (&)[1]) {}
+template <> SLICQ_DEVFN void dft<1, true>(cpx (&)[1]) {}
 '''
 
 
@@ -344,8 +418,8 @@ def generate() -> str:
     for n in COMPLEX_SIZES:
         for inv in (False, True):
             body, flops = gen_complex(n, inv)
-            parts.append(f"// DFT-{n} {'inverse' if inv else 'forward'}: {flops} flops")
-            parts.append(f"template <> SLICQ_DEVFN void dft<{n}, {'true' if inv else 'false'}>(float2 (&v)[{n}]) {{")
+            parts.append(f"// DFT-{n} {'inverse' if inv else 'forward'}: {flops} packed instructions")
+            parts.append(f"template <> SLICQ_DEVFN void dft<{n}, {'true' if inv else 'false'}>(cpx (&v)[{n}]) {{")
             parts.extend(body)
             parts.append("}\n")
     for p in REAL_SYM_PRIMES:
@@ -358,8 +432,10 @@ def generate() -> str:
 
 
 def codelet_flops(n: int) -> int:
-    e = Emitter()
-    dft(e, [(f"r{i}", f"i{i}") for i in range(n)], -1)
+    e = CEmitter()
+    y = dft(e, [CV(f"x{i}") for i in range(n)], -1)
+    for v in y:
+        e.plain(v)
     return e.flops
 
 
@@ -409,18 +485,15 @@ def check() -> None:
     worst = 0.0
     for n in COMPLEX_SIZES:
         for inv in (False, True):
-            e = Emitter()
-            x = [(f"xr{i}", f"xi{i}") for i in range(n)]
-            y = dft(e, x, +1 if inv else -1)
-            vals = rs.randn(n) + 1j * rs.randn(n)
-            env = {}
-            for i in range(n):
-                env[f"xr{i}"] = np.float32(vals[i].real)
-                env[f"xi{i}"] = np.float32(vals[i].imag)
+            e = CEmitter()
+            y = dft(e, [CV(f"x{i}") for i in range(n)], +1 if inv else -1)
+            outs = [e.plain(v) for v in y]
+            vals = (rs.randn(n) + 1j * rs.randn(n)).astype(np.complex64)
+            env = {f"x{i}": complex(vals[i]) for i in range(n)}
             env = e.evaluate(env)
-            got = np.asarray([complex(env[r], env[i]) for r, i in y])
-            v32 = np.asarray([complex(env[f"xr{i}"], env[f"xi{i}"]) for i in range(n)])
-            ref = np.fft.ifft(v32) * n if inv else np.fft.fft(v32)
+            got = np.asarray([env[o] for o in outs])
+            v64 = vals.astype(np.complex128)
+            ref = np.fft.ifft(v64) * n if inv else np.fft.fft(v64)
             err = np.abs(got - ref).max() / np.abs(ref).max()
             worst = max(worst, err)
             assert err < 2e-6, (n, inv, err)
@@ -443,7 +516,7 @@ def check() -> None:
                 sv = sinpi2(n * k, p)
                 bk = e.mulc(b[n], sv) if bk is None else e.fmac(b[n], sv, bk)
             outs[k] = (ak, bk)
-        env = e.evaluate(env)
+        env = _scalar_evaluate(e, env)
         F = np.fft.fft(vals.astype(np.float64))
         for k in range(1, h + 1):
             A = env[outs[k][0]]; B = env[outs[k][1]]
