@@ -36,6 +36,9 @@ from typing import Dict, List, Tuple
 # sizes emitted
 COMPLEX_SIZES = [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 22, 23, 24, 28, 32]
 REAL_SYM_PRIMES = [29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73]
+# streamed prime transforms split by outputs over NP threads: (P, NP)
+PRIME_PARTS = [(43, 2), (29, 2), (31, 2), (37, 2), (41, 2), (43, 3), (47, 3), (53, 3), (59, 3), (61, 3),
+               (67, 4), (71, 4), (73, 4)]
 
 
 def cospi2(num: int, den: int) -> float:
@@ -387,6 +390,104 @@ def gen_real_sym(p: int) -> Tuple[List[str], int]:
     return lines, e.flops
 
 
+def part_bounds(p: int, nparts: int) -> List[int]:
+    """pairs k = 1..(p-1)/2 dealt to nparts consecutive groups: part q owns k in [kb[q], kb[q+1])"""
+    h = (p - 1) // 2
+    base, extra = divmod(h, nparts)
+    kb = [1]
+    for q in range(nparts):
+        kb.append(kb[-1] + base + (1 if q < extra else 0))
+    assert kb[-1] == h + 1
+    return kb
+
+
+def gen_prime_part(p: int, nparts: int, part: int, inv: bool) -> Tuple[List[str], int, int]:
+    """Streamed symmetric direct form of the DFT-p, outputs k in this part's range (and p-k; part 0 also
+    k = 0).  Inputs come one pair (n, p-n) at a time from `s.ld(n)`; the accumulators are the only
+    long-lived registers.  Returns (body lines, packed instruction count, number of outputs)."""
+    h = (p - 1) // 2
+    kb = part_bounds(p, nparts)
+    ks = list(range(kb[part], kb[part + 1]))
+    L: List[str] = []
+    ops = 0
+    L.append("    const cpx x0 = s.ld(0);")
+    if part == 0:
+        L.append("    cpx S = x0;")
+    for k in ks:
+        L.append(f"    cpx A{k} = x0, B{k};")
+    for n in range(1, h + 1):
+        L.append("    {")
+        L.append(f"        const cpx xu = s.ld({n}), xd = s.ld({p - n});")
+        L.append("        const cpx a = cadd(xu, xd), b = csub(xu, xd);")
+        ops += 2
+        if part == 0:
+            L.append("        S = cadd(S, a);")
+            ops += 1
+        for k in ks:
+            c = cospi2(n * k, p)
+            sv = sinpi2(n * k, p)
+            L.append(f"        A{k} = cfmar(a, {lit(c)}, A{k});")
+            if n == 1:
+                L.append(f"        B{k} = cmulr(b, {lit(sv)});")
+            else:
+                L.append(f"        B{k} = cfmar(b, {lit(sv)}, B{k});")
+            ops += 2
+        L.append("    }")
+    o = 0
+    if part == 0:
+        L.append("    o[0] = S;")
+        o = 1
+    for k in ks:
+        # forward: X[k] = A - iB, X[p-k] = A + iB ; inverse: the opposite
+        lo, hi = ("caddi", "csubi") if inv else ("csubi", "caddi")
+        L.append(f"    o[{o}] = {lo}(A{k}, B{k});")
+        L.append(f"    o[{o + 1}] = {hi}(A{k}, B{k});")
+        o += 2
+        ops += 2
+    return L, ops, o
+
+
+def gen_prime_parts(p: int, nparts: int) -> List[str]:
+    out: List[str] = []
+    kb = part_bounds(p, nparts)
+    nout = max(2 * (kb[q + 1] - kb[q]) + (1 if q == 0 else 0) for q in range(nparts))
+    for inv in (False, True):
+        tag = "i" if inv else "f"
+        for q in range(nparts):
+            body, ops, _ = gen_prime_part(p, nparts, q, inv)
+            out.append(f"// DFT-{p} {'inverse' if inv else 'forward'}, part {q} of {nparts}: {ops} packed instructions")
+            out.append(f"template <class SRC> SLICQ_DEVFN void dftp_{p}_{nparts}_{q}_{tag}(SRC& s, cpx (&o)[{nout}]) {{")
+            out.extend(body)
+            out.append("}\n")
+        out.append(f"template <> struct Dftp<{p}, {nparts}, {'true' if inv else 'false'}> {{")
+        out.append(f"    static constexpr int NOUT = {nout};")
+        out.append("    template <class SRC> static SLICQ_DEVFN void run(int part, SRC& s, cpx (&o)[NOUT]) {")
+        out.append("        switch (part) {")
+        for q in range(nparts):
+            out.append(f"            case {q}: dftp_{p}_{nparts}_{q}_{tag}(s, o); break;")
+        out.append("            default: break;")
+        out.append("        }")
+        out.append("    }")
+        out.append("    // d.st(k, value): output index k of the transform")
+        out.append("    template <class DST> static SLICQ_DEVFN void store(int part, DST& d, const cpx (&o)[NOUT]) {")
+        out.append("        switch (part) {")
+        for q in range(nparts):
+            sts = []
+            o = 0
+            if q == 0:
+                sts.append("d.st(0, o[0]);")
+                o = 1
+            for k in range(kb[q], kb[q + 1]):
+                sts.append(f"d.st({k}, o[{o}]); d.st({p - k}, o[{o + 1}]);")
+                o += 2
+            out.append(f"            case {q}: " + " ".join(sts) + " break;")
+        out.append("            default: break;")
+        out.append("        }")
+        out.append("    }")
+        out.append("};\n")
+    return out
+
+
 HEADER = '''// GENERATED by gen_codelets.py -- do not edit by hand.
 // Register-resident DFT codelets for the sliCQT kernels (see gen_codelets.py docstring).
 #pragma once
@@ -408,6 +509,13 @@ template <int N, bool INV> SLICQ_DEVFN void dft(float2 (&v)[N]) {
 //   out[0] = sum_n x[n];  out[k*stride] = x0 + sum a_n cos(2 pi nk/P);  out[(P-k)*stride] = sum b_n sin(2 pi nk/P)
 template <int P> SLICQ_DEVFN void rdft_sym(const float (&x)[P], float* out, int stride);
 
+// Dftp<P, NP, INV>: DFT of prime length P streamed from `SRC::ld(n)` and split BY OUTPUTS over NP threads
+// ("parts"; part q accumulates the outputs k and P-k of its pair range, part 0 also k = 0):
+//   run(part, src, o)   reads all P inputs (one pair (n, P-n) at a time), leaves the part's outputs in o[]
+//   store(part, dst, o) hands them to `DST::st(k, value)`
+// Twiddles are immediates, the accumulators the only long-lived registers (2 * pairs + 1 complex).
+template <int P, int NP, bool INV> struct Dftp;
+
 template <> SLICQ_DEVFN void dft<1, false>(cpx (&)[1]) {}
 template <> SLICQ_DEVFN void dft<1, true>(cpx (&)[1]) {}
 '''
@@ -422,6 +530,8 @@ def generate() -> str:
             parts.append(f"template <> SLICQ_DEVFN void dft<{n}, {'true' if inv else 'false'}>(cpx (&v)[{n}]) {{")
             parts.extend(body)
             parts.append("}\n")
+    for (p, nparts) in PRIME_PARTS:
+        parts.extend(gen_prime_parts(p, nparts))
     for p in REAL_SYM_PRIMES:
         body, flops = gen_real_sym(p)
         parts.append(f"// real symmetric half-DFT, prime {p}: {flops} flops")

@@ -73,6 +73,16 @@ SLICQ_DEVFN void bins_body(const SlicqBinsParams& p, unsigned char* smem) {
     if (j.u0 >= j.u1) return;
     j.F = b.n_bins; j.gt = b.gt; j.first_bin = b.first_bin; j.rs0 = p.rs0; j.S = p.S; j.x_rows = SYNTH ? p.x_rows : 0;
     j.aux = SYNTH ? (b.mptr != nullptr) : (b.nptr != nullptr);
+    if (SYNTH) {
+        // positions of the T planes that no bin covers: zero them for this job's units (see SlicqDeviceTables)
+        const int nu = j.u1 - j.u0;
+        for (int t = threadIdx.x; t < nu * b.gap_n; t += blockDim.x) {
+            const int u = t / b.gap_n, e = t - u * b.gap_n;
+            const int2 g = __ldg(p.t.gaps + b.gap_first + e);
+            float2* o = p.spec + (long long)(j.u0 + u) * p.spec_stride + g.x;
+            for (int c = 0; c < g.y; ++c) o[c] = make_float2(0.f, 0.f);
+        }
+    }
     switch (b.M) {
 #define SLICQ_FFT_SIZE(M_, K_, A_, B_) \
     case M_: JobRunner<M_, K_, A_, B_, SYNTH>::run(p, b, j, smem); break;
@@ -106,12 +116,18 @@ extern "C" int slicq_bins_threads(void) { return SLICQ_BINS_THREADS; }
 // host-side launcher (called from slicq_api.cu) -----------------------------------------------
 extern "C" int slicq_launch_bins(const SlicqBinsParams* p, int n_jobs, int smem_bytes, int synth, cudaStream_t s) {
     if (n_jobs <= 0) return 0;
-    static int attr_done = 0;
-    if (!attr_done) {
-        SLICQ_SET_SMEM(bins_fwd_kernel, 100 * 1024);
-        SLICQ_SET_SMEM(bins_inv_kernel, 100 * 1024);
-        attr_done = 1;
+#ifndef SLICQ_EMU
+    {   // cudaFuncSetAttribute is per device
+        static bool done[64] = {false};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -3;
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            if (SLICQ_SET_SMEM(bins_fwd_kernel, 100 * 1024) != cudaSuccess) return -3;
+            if (SLICQ_SET_SMEM(bins_inv_kernel, 100 * 1024) != cudaSuccess) return -3;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
     }
+#endif
     if (synth) {
         SLICQ_LAUNCH(bins_inv_kernel, dim3(n_jobs), dim3(SLICQ_BINS_THREADS), smem_bytes, s, *p);
     } else {

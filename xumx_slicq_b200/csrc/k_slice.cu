@@ -1,55 +1,40 @@
-// Stage 1 (Tukey slicing + slice FFT), stage 3b (spectrum gather + slice IFFT) and stage 4
-// (50 % overlap-add) of the sliCQT path.
+// Stage 1 (Tukey slicing + slice FFT), stage 3b (plane sum + slice IFFT) and stage 4 (50 % overlap-add)
+// of the sliCQT path.  One CTA per (row, slice) unit; the whole length-L real transform lives in shared memory.
 //
-// The length-L real slice transform (L = 18060 = 2 * 43*15*14 for the pretrained Bark
-// parameters) runs as ONE complex FFT of length N = L/2 = 9030 held in shared memory, computed
-// with the Good-Thomas prime-factor algorithm on the 3-D index space 43 x 15 x 14: the three
-// factors are pairwise coprime, so there are NO twiddle multiplications between the passes --
-// input index n lives at (n mod 43, n mod 15, n mod 14), output index
-// k = (210 k1 + 602 k2 + 645 k3) mod 9030 lives at (k1, k2, k3).  The load / store phases visit
-// indices tid + i * blockDim and keep the three residues of the index in registers (Pfa3::Walk).
-//   pass A  43-point symmetric real half-transforms down the first axis (rdft_sym<43>), the real
-//           and the imaginary part of a column on separate threads, in place
-//   pass B  combine (A_k -/+ i B_k) fused with the 15-point codelet, rows k1 and 43-k1 together
-//   pass C  14-point codelet along the contiguous axis
-// followed (forward) / preceded (inverse) by the even/odd split that turns the N-point complex
-// transform into the L-point real one.
+// The length-L real slice transform (L = 18060 for the pretrained Bark parameters) runs as ONE complex FFT of
+// length N = L/2 = 9030 = 43 * 15 * 14 with the Good-Thomas prime-factor algorithm: the factors are pairwise
+// coprime, so there are NO twiddle multiplications between the passes.  Round 2 design ("natural-order PFA"):
+// the index permutations of the algorithm are folded into the first and the last pass, so that there is no
+// separate permuting load / store phase and no per-element index arithmetic anywhere:
 //
-// Shared-memory layout: element (a, b, c) at a*SA + b*SB + c (float2 units) with SB = 15 and
-// SA = 227: SA odd makes the "lane <-> a" task orders of passes B and C conflict-free for 64-bit
-// accesses, and SA + SB + 1 odd does the same for the permuted load / store phases.
+//   Ruritanian side  index = (210 i1 + 43 m) mod N, m = (14 i2 + 15 i3) mod 210.  A thread of pass A owns the
+//                    column m (lanes <-> consecutive m: stride 43 words, conflict free) and finds its 43
+//                    elements in NATURAL order at 43 m + 210 i1, minus N from the wrap point on (one select).
+//   CRT side         (i1, i2, i3) = (index mod 43, mod 15, mod 14).  A thread of pass C owns the orbit
+//                    {t + 645 j} of the last axis (lanes <-> consecutive t: coalesced global access); element j
+//                    of the orbit has i3 = (t + j) mod 14, a rotation that costs one select per element.
+//
+//   analysis   x (global, CRT side) -> pass C (Tukey window on load, DFT-14) -> pass B (DFT-15) -> pass A (DFT-43)
+//              -> natural order in shared memory -> even/odd split -> padded half spectrum H (global)
+//   synthesis  two bin planes of T (global) summed in natural order -> Hermitian pre-processing -> pass A -> pass B
+//              -> pass C, whose outputs go straight to y (store for even slices, red.add for odd slices)
+//
+// Pass A is the 43-point symmetric direct form streamed over the inputs and split BY OUTPUTS over two threads per
+// column (Dftp<43, 2>, gen_codelets.py): 22 complex accumulators per thread, all twiddles immediates, and every
+// operation one packed FFMA2 / FADD2.  Passes B and C are the packed straight-line codelets dft<15> / dft<14>.
 //
 // reference: nsgt/slicing.py:7-72 + nsgt/nsgtf.py:40 (forward), nsgt/nsigtf.py:93-103 +
 //            nsgt/unslicing.py:33-69 + nsgt/slicq.py:207-230 (inverse); closed forms in DESIGN.md.
 #include "slicq_common.cuh"
 #include "dft_codelets.cuh"
 
-// optional per-phase timing (tuning builds only, -DSLICQ_PHASE_TIMING): thread 0 of every CTA stores
-// clock64() at the phase boundaries into a buffer registered with slicq_debug_set_timing()
-// (tools/phase_timing.py).  Compiled out of the product build.
-#if defined(SLICQ_PHASE_TIMING) && !defined(SLICQ_EMU)
-__device__ long long* g_phase_buf = nullptr;
-#define PHASE_MARK(i) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = clock64(); } while (0)
-#define PHASE_CLOCK() clock64()
-#define PHASE_STORE_T(t, i, v) do { if (threadIdx.x == (t) && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = (v); } while (0)
-#define PHASE_STORE(i, v) do { if (threadIdx.x == 0 && g_phase_buf) g_phase_buf[(long long)blockIdx.x * 16 + (i)] = (v); } while (0)
-extern "C" int slicq_debug_set_timing(long long* buf) { return (int)cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof buf); }
-#else
-#define PHASE_MARK(i) do {} while (0)
-#define PHASE_CLOCK() 0LL
-#define PHASE_STORE(i, v) do {} while (0)
-#define PHASE_STORE_T(t, i, v) do {} while (0)
-extern "C" int slicq_debug_set_timing(long long*) { return -1; }
-#endif
-
-#ifndef SLICQ_GATHER_UG
-#define SLICQ_GATHER_UG 3   // spectrum pairs per thread and round of the synthesis gather
-#endif
-#ifndef SLICQ_FWD_LOADS
-#define SLICQ_FWD_LOADS 6
-#endif
 #ifndef SLICQ_SLICE_THREADS
-#define SLICQ_SLICE_THREADS 384
+#define SLICQ_SLICE_THREADS 448
+#endif
+// tuning experiments only (results invalid): bit 0 skips the load phases of the synthesis slice kernel, bit 1 pass A,
+// bit 2 pass B, bit 3 the output stores
+#ifndef SLICQ_DBG_SKIP
+#define SLICQ_DBG_SKIP 0
 #endif
 
 namespace {
@@ -61,327 +46,314 @@ constexpr int cmodinv(int a, int m) {
     return 0;
 }
 
-template <int P1_, int P2_, int P3_>
-struct Pfa3 {
-    static constexpr int P1 = P1_, P2 = P2_, P3 = P3_;
-    static constexpr int N = P1 * P2 * P3;
-    static constexpr int SB = (P3 % 2 == 0) ? P3 + 1 : P3 + 2;              // odd
-    static constexpr int SA = (P2 * SB) % 2 == 1 ? P2 * SB + 2 : P2 * SB + 1;  // odd, > P2*SB
-    static constexpr int SMEM_ELEMS = P1 * SA;
-    static constexpr int I1 = cmodinv(N / P1, P1), I2 = cmodinv(N / P2, P2), I3 = cmodinv(N / P3, P3);
-    // shared-memory slot of FFT input index n / output index k: a few integer multiplies (constant
-    // divisors) instead of a table lookup, so the permuted phases have no dependent memory access
-    static __host__ SLICQ_DEVFN int pos_in(int n) { return (n % P1) * SA + (n % P2) * SB + (n % P3); }
-    static __host__ SLICQ_DEVFN int pos_out(int k) { return ((k * I1) % P1) * SA + ((k * I2) % P2) * SB + ((k * I3) % P3); }
-    // Residue walker: the load / store phases visit indices tid + i * blockDim, so they keep the three
-    // residues of the index and advance them by a constant (one add and one conditional subtract
-    // each) instead of dividing three times per element.
-    struct Walk { int a, b, c; };
-    static SLICQ_DEVFN Walk walk_in(int n) { Walk w; w.a = n % P1; w.b = n % P2; w.c = n % P3; return w; }
-    static SLICQ_DEVFN Walk walk_out(int k) { Walk w; w.a = (k * I1) % P1; w.b = (k * I2) % P2; w.c = (k * I3) % P3; return w; }
-    static SLICQ_DEVFN Walk add_res(Walk w, int da, int db, int dc) {   // da < P1, db < P2, dc < P3
-        w.a += da; if (w.a >= P1) w.a -= P1;
-        w.b += db; if (w.b >= P2) w.b -= P2;
-        w.c += dc; if (w.c >= P3) w.c -= P3;
-        return w;
-    }
-    static SLICQ_DEVFN Walk step_in(Walk w, int d) { return add_res(w, d % P1, d % P2, d % P3); }     // index + d, d >= 0
-    static SLICQ_DEVFN Walk step_out(Walk w, int d) { return add_res(w, ((d % P1) * I1) % P1, ((d % P2) * I2) % P2, ((d % P3) * I3) % P3); }
-    static SLICQ_DEVFN Walk neg(Walk w) {   // residues of N - index
-        w.a = w.a ? P1 - w.a : 0; w.b = w.b ? P2 - w.b : 0; w.c = w.c ? P3 - w.c : 0;
-        return w;
-    }
-    static SLICQ_DEVFN int slot(Walk w) { return w.a * SA + w.b * SB + w.c; }
+template <int P1_, int P2_, int P3_, int NP_, int SB_, int SA_>
+struct PfaNat {
+    static constexpr int P1 = P1_, P2 = P2_, P3 = P3_, NP = NP_;
+    static constexpr int N = P1 * P2 * P3, Q = P2 * P3, C3 = N / P3;
+    static constexpr int SB = SB_, SA = SA_;                 // pitches of the (i1, i2, i3) layout between the passes
+    static constexpr int SLOT = (Q + 31) / 32 * 32;          // pass A: threads per part (warp multiple >= Q)
+    static constexpr int SMEM_ELEMS = (P1 * SA > N + 2 ? P1 * SA : N + 2);
+    static constexpr int I2 = cmodinv(P3, P2), I3 = cmodinv(P2, P3);   // m -> (i2, i3) = (I2 m mod P2, I3 m mod P3)
+    static_assert(C3 % P3 == 1, "orbit rotation of the last axis assumes (N / P3) mod P3 == 1");
+    static_assert(SA >= P2 * SB && SB >= P3, "pitches too small");
+    static_assert(NP * SLOT <= SLICQ_SLICE_THREADS, "pass A needs NP * SLOT threads");
 };
+typedef PfaNat<43, 15, 14, 2, 16, 243> Pfa9030;
+
+// pass A sources / destinations (Dftp<>::run / store)
+template <class PF> struct ColNat {        // column m in natural order: element i1 at 43 m + 210 i1 (mod N)
+    float2* lo; float2* hi; int nw;
+    SLICQ_DEVFN ColNat(float2* Z, int m) {
+        lo = Z + PF::P1 * m;
+        hi = lo - PF::N;
+        nw = (PF::N - PF::P1 * m + PF::Q - 1) / PF::Q;       // first i1 past the wrap
+    }
+    SLICQ_DEVFN cpx ld(int i) const { return cpx_ld((i >= nw ? hi : lo) + PF::Q * i); }
+    SLICQ_DEVFN void st(int i, cpx v) const { cpx_st((i >= nw ? hi : lo) + PF::Q * i, v); }
+};
+template <class PF> struct ColL2 {         // column (i2, i3) of the pitched layout: element i1 at i1 * SA + i2 * SB + i3
+    float2* p;
+    SLICQ_DEVFN ColL2(float2* Z, int m) { p = Z + ((PF::I2 * m) % PF::P2) * PF::SB + ((PF::I3 * m) % PF::P3); }
+    SLICQ_DEVFN cpx ld(int i) const { return cpx_ld(p + PF::SA * i); }
+    SLICQ_DEVFN void st(int i, cpx v) const { cpx_st(p + PF::SA * i, v); }
+};
+
+// pass A: DFT-P1 of every column; SRC / DST = the layout the pass reads / writes (both alias Z: all reads
+// complete before the first write)
+template <class PF, bool INV, class SRC, class DST>
+SLICQ_DEVFN void pass_a(float2* Z) {
+    typedef Dftp<PF::P1, PF::NP, INV> D;
+    const int part = threadIdx.x / PF::SLOT, m = threadIdx.x - part * PF::SLOT;
+    const bool act = part < PF::NP && m < PF::Q;
+    cpx o[D::NOUT];
+    if (act) { SRC s(Z, m); D::run(part, s, o); }
+    __syncthreads();
+    if (act) { DST d(Z, m); D::store(part, d, o); }
+    __syncthreads();
+}
+
+// pass B: DFT-P2 along i2 for fixed (i1, i3), in place; lanes <-> i1 (pitch SA odd: conflict free)
 template <class PF, bool INV>
-SLICQ_DEVFN void pfa_passes(float2* Z) {
-    constexpr int P1 = PF::P1, P2 = PF::P2, P3 = PF::P3, SA = PF::SA, SB = PF::SB;
-    float* Zf = reinterpret_cast<float*>(Z);
-    // ---- pass A: lane <-> (column, re|im): consecutive words of one row
-    for (int t = threadIdx.x; t < P2 * P3 * 2; t += blockDim.x) {
-        const int c2 = t & 1, col = t >> 1;
-        const int b = col / P3, c = col - b * P3;
-        float* base = Zf + (b * SB + c) * 2 + c2;
-        float x[P1];
+SLICQ_DEVFN void pass_b(float2* Z) {
+    for (int t = threadIdx.x; t < PF::P1 * PF::P3; t += SLICQ_SLICE_THREADS) {
+        const int i3 = t / PF::P1, i1 = t - i3 * PF::P1;
+        float2* p = Z + i1 * PF::SA + i3;
+        cpx v[PF::P2];
 #pragma unroll
-        for (int a = 0; a < P1; ++a) x[a] = base[a * SA * 2];
-        rdft_sym<P1>(x, base, SA * 2);
-    }
-    __syncthreads();
-    PHASE_MARK(2);
-    // ---- pass B: lane <-> kk (row pair), pitch SA odd
-    constexpr int H1 = (P1 - 1) / 2;
-    for (int t = threadIdx.x; t < (H1 + 1) * P3; t += blockDim.x) {
-        const int c = t / (H1 + 1), kk = t - c * (H1 + 1);
-        float2* rp = Z + kk * SA + c;
-        float2* rm = Z + (P1 - kk) * SA + c;
-        float2 xp[P2], xm[P2];
+        for (int b = 0; b < PF::P2; ++b) v[b] = cpx_ld(p + b * PF::SB);
+        dft<PF::P2, INV>(v);
 #pragma unroll
-        for (int b = 0; b < P2; ++b) {
-            const float2 a = rp[b * SB];
-            if (kk == 0) {
-                xp[b] = a;
-            } else {
-                const float2 q = rm[b * SB];  // (B_re, B_im)
-                if (!INV) {
-                    xp[b] = make_float2(a.x + q.y, a.y - q.x);
-                    xm[b] = make_float2(a.x - q.y, a.y + q.x);
-                } else {
-                    xp[b] = make_float2(a.x - q.y, a.y + q.x);
-                    xm[b] = make_float2(a.x + q.y, a.y - q.x);
-                }
-            }
-        }
-        dft<P2, INV>(xp);
-#pragma unroll
-        for (int b = 0; b < P2; ++b) rp[b * SB] = xp[b];
-        if (kk != 0) {
-            dft<P2, INV>(xm);
-#pragma unroll
-            for (int b = 0; b < P2; ++b) rm[b * SB] = xm[b];
-        }
-    }
-    __syncthreads();
-    PHASE_MARK(3);
-    // ---- pass C: lane <-> a, pitch SA odd
-    for (int t = threadIdx.x; t < P1 * P2; t += blockDim.x) {
-        const int b = t / P1, a = t - b * P1;
-        float2* r = Z + a * SA + b * SB;
-        float2 v[P3];
-#pragma unroll
-        for (int c = 0; c < P3; ++c) v[c] = r[c];
-        dft<P3, INV>(v);
-#pragma unroll
-        for (int c = 0; c < P3; ++c) r[c] = v[c];
+        for (int b = 0; b < PF::P2; ++b) cpx_st(p + b * PF::SB, v[b]);
     }
     __syncthreads();
 }
 
 }  // namespace
 
-typedef Pfa3<43, 15, 14> Pfa9030;
-
 // ------------------------------------------------------------------------------------------
 // stage 1: one CTA per (row, slice).  x -> padded half spectrum H_ext[pad_l + f], f in [-pad_l, N + pad_r]
 template <class PF>
 __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
-    constexpr int N = PF::N;
+    constexpr int N = PF::N, NT = SLICQ_SLICE_THREADS, P3 = PF::P3, C3 = PF::C3;
     const int rsl = blockIdx.x;
     const int rs = p.rs0 + rsl;
     const int row = rs / p.S, k = rs - row * p.S;
     const long long s0 = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;  // x index of slice sample 0
-    PHASE_MARK(0);
     const float* __restrict__ xr = p.x + row * p.x_row_stride;
     const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
-    const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;
-    // zero part of the window: no loads
-    constexpr int NT = SLICQ_SLICE_THREADS;
-    {
-        typename PF::Walk wz = PF::walk_in(threadIdx.x);
-        for (int e = threadIdx.x; e < e_lo; e += NT) { Z[PF::slot(wz)] = make_float2(0.f, 0.f); wz = PF::step_in(wz, NT); }
-        wz = PF::walk_in(e_hi + threadIdx.x);
-        for (int e = e_hi + threadIdx.x; e < N; e += NT) { Z[PF::slot(wz)] = make_float2(0.f, 0.f); wz = PF::step_in(wz, NT); }
-    }
-    PHASE_MARK(7);
-    const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;   // x range touched by the window support
-    const bool interior = sa >= 0 && sb <= p.T;
-    const bool vec = ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
-    constexpr int U = SLICQ_FWD_LOADS;   // sample pairs in flight per thread: the phase costs one memory round trip per U * NT pairs
-    typename PF::Walk wl = PF::walk_in(e_lo + threadIdx.x);
-    if (interior && vec) {
+    const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;       // sample pairs with a non-zero window
+    const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;             // x range touched by the window support
+    const bool fast = sa >= 0 && sb <= p.T && ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
+    // ---- windowed slice -> Z in natural order (coalesced loads; the zero part of the window is not read)
+    if (fast) {
         const float2* __restrict__ x2 = reinterpret_cast<const float2*>(xr + s0);
-        for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += U * NT) {
-            float2 v[U], w[U];
+        constexpr int U = 5;
+        for (int e0 = threadIdx.x; e0 < N; e0 += U * NT) {
+            float2 xv[U], wv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * NT;
-                if (e < e_hi) { w[u] = __ldg(tw2 + e); v[u] = __ldg(x2 + e); }
+                if (e >= e_lo && e < e_hi) { xv[u] = __ldg(x2 + e); wv[u] = __ldg(tw2 + e); }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * NT;
-                if (e < e_hi) Z[PF::slot(PF::step_in(wl, u * NT))] = make_float2(v[u].x * w[u].x, v[u].y * w[u].y);
+                if (e < N) Z[e] = (e >= e_lo && e < e_hi) ? make_float2(xv[u].x * wv[u].x, xv[u].y * wv[u].y) : make_float2(0.f, 0.f);
             }
-            wl = PF::step_in(wl, U * NT);
         }
     } else {
-        for (int e = e_lo + threadIdx.x; e < e_hi; e += NT) {
-            const long long s = s0 + 2 * e;
-            const float2 w = __ldg(tw2 + e);
+        for (int e = threadIdx.x; e < N; e += NT) {
+            const long long sx = s0 + 2 * e;
+            const float2 wv = __ldg(tw2 + e);
             float a = 0.f, b = 0.f;
-            if (s >= 0 && s < p.T) a = __ldg(xr + s) * w.x;
-            if (s + 1 >= 0 && s + 1 < p.T) b = __ldg(xr + s + 1) * w.y;
-            Z[PF::slot(wl)] = make_float2(a, b);
-            wl = PF::step_in(wl, NT);
+            if (sx >= 0 && sx < p.T) a = __ldg(xr + sx) * wv.x;
+            if (sx + 1 >= 0 && sx + 1 < p.T) b = __ldg(xr + sx + 1) * wv.y;
+            Z[e] = make_float2(a, b);
         }
     }
-    PHASE_MARK(4);
     __syncthreads();
-    PHASE_MARK(1);
-    pfa_passes<PF, false>(Z);
-    PHASE_MARK(5);
-    // even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O); mirrored margins for the bins
+    // ---- pass C (first): thread t owns the orbit {t + C3 j} of the natural order; element j has i3 = (t + j) mod P3.
+    // The outputs go to the pitched layout, which aliases the natural one: all tasks of a thread stay in registers
+    // until every thread has read its inputs.
+    {
+        constexpr int NRC = (C3 + NT - 1) / NT;
+        cpx v[NRC][P3];
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) {
+            const int t = threadIdx.x + r * NT;
+            if (t < C3) {
+                const int s = t % P3;
+                const int j0 = s ? P3 - s : 0, w = P3 - j0;      // v[c] = element j0 + c (mod P3); wraps for c >= w
+                const float2* za = Z + t + j0 * C3;
+                const float2* zb = za - N;
+#pragma unroll
+                for (int c = 0; c < P3; ++c) v[r][c] = cpx_ld((c >= w ? zb : za) + c * C3);
+                dft<P3, false>(v[r]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) {
+            const int t = threadIdx.x + r * NT;
+            if (t < C3) {
+                float2* o = Z + (t % PF::P1) * PF::SA + (t % PF::P2) * PF::SB;
+#pragma unroll
+                for (int c = 0; c < P3; ++c) cpx_st(o + c, v[r][c]);
+            }
+        }
+    }
+    __syncthreads();
+    pass_b<PF, false>(Z);
+    pass_a<PF, false, ColL2<PF>, ColNat<PF> >(Z);
+    // ---- even/odd split: H[k] = E + w^k O, H[N-k] = conj(E - w^k O); mirrored margins for the bins
     // that reach below DC / above Nyquist (Hermitian symmetry of a real slice)
     float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
     const int pad_l = p.t.pad_l, pad_r = p.t.pad_r;
-    const float sc = p.t.spec_scale, se = p.t.ends_scale;
+    const float sc = 0.5f * p.t.spec_scale, se = p.t.ends_scale;
     const float mir = p.t.adjoint ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
-    constexpr int UP = 4;
-    typename PF::Walk wp = PF::walk_out(threadIdx.x);
-    for (int kk0 = threadIdx.x; kk0 <= N / 2; kk0 += UP * NT) {
-        int pk[UP], pn[UP];
-        float2 wk[UP];
+    constexpr int NP2 = (N / 2 + NT) / NT;      // pairs (k, N-k) per thread
+    float2 wkv[NP2];
 #pragma unroll
-        for (int u = 0; u < UP; ++u) {
-            const int kk = kk0 + u * NT;
-            if (kk <= N / 2) {
-                const typename PF::Walk wq = PF::step_out(wp, u * NT);
-                pk[u] = PF::slot(wq); pn[u] = PF::slot(PF::neg(wq));    // slots of output kk and N - kk (kk = 0: both slot 0)
-                wk[u] = __ldg(p.t.post_tw + kk);
-            }
-        }
-        wp = PF::step_out(wp, UP * NT);
+    for (int u = 0; u < NP2; ++u) {
+        const int kk = threadIdx.x + u * NT;
+        if (kk <= N / 2) wkv[u] = __ldg(p.t.post_tw + kk);
+    }
 #pragma unroll
-        for (int u = 0; u < UP; ++u) {
-            const int kk = kk0 + u * NT;
-            if (kk > N / 2) continue;
-            const float2 zk = Z[pk[u]];
-            if (kk == 0) {
-                H[0] = make_float2((zk.x + zk.y) * se, 0.f);
-                H[N] = make_float2((zk.x - zk.y) * se, 0.f);
-            } else {
-                const float2 zn = Z[pn[u]];
-                const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-                const float2 O = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));  // -(i/2)(zk - conj zn)
-                const float2 t = cmul(wk[u], O);
-                const float2 hk = make_float2((E.x + t.x) * sc, (E.y + t.y) * sc);
-                const float2 hn = make_float2((E.x - t.x) * sc, -(E.y - t.y) * sc);
-                H[kk] = hk;
-                H[N - kk] = hn;
-                if (kk <= pad_l) H[-kk] = make_float2(hk.x * mir, -hk.y * mir);
-                if (kk <= pad_r) H[N + kk] = make_float2(hn.x * mir, -hn.y * mir);
-            }
+    for (int u = 0; u < NP2; ++u) {
+        const int kk = threadIdx.x + u * NT;
+        if (kk > N / 2) continue;
+        const cpx zk = cpx_ld(Z + kk);
+        if (kk == 0) {
+            const float a = cpx_re(zk), b = cpx_im(zk);
+            H[0] = make_float2((a + b) * se, 0.f);
+            H[N] = make_float2((a - b) * se, 0.f);
+        } else {
+            const cpx zn = cpx_ld(Z + N - kk);
+            const float2 wk = wkv[u];
+            const cpx E = caddc(zk, zn);                    // zk + conj(zn)           (= 2 E)
+            const cpx D = csubc(zk, zn);                    // zk - conj(zn)           (= 2 i O)
+            const cpx t = cmulw(D, wk);                     // w^k (zk - conj zn) = 2 i w^k O
+            // H[k] = E + w^k O = (2E - i t) / 2 ; H[N-k] = conj(E - w^k O) = conj(2E + i t) / 2
+            const cpx hk = cmulr(csubi(E, t), sc);
+            const cpx hn = cmulr(cconjp(caddi(E, t)), sc);
+            cpx_st(H + kk, hk);
+            cpx_st(H + N - kk, hn);
+            if (kk <= pad_l) cpx_st(H - kk, cmulr(cconjp(hk), mir));
+            if (kk <= pad_r) cpx_st(H + N + kk, cmulr(cconjp(hn), mir));
         }
     }
-    PHASE_MARK(6);
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 3b + 4: one CTA per (row, slice).  packed windowed bin spectra T -> slice signal u[L],
-// overlap-added straight into y:  y[(k-1)*hop + p] += u_k[p].  Every output sample is the sum of
-// exactly two slices, one even and one odd: the launch with parity 0 STORES the even slices, the
-// launch with parity 1 (stream-ordered after it) ADDS the odd ones with fire-and-forget reductions
-// (red.global.add: every location receives exactly one addition, so no ordering question arises) --
-// no intermediate slice buffer, and a two-term sum is order independent (bitwise reproducible).
-// (reference: nsgt/unslicing.py:33-69, nsgt/slicq.py:207-230)
+// stage 3b + 4: one CTA per (row, slice).  T row = two planes of windowed bin spectra (even bins / odd bins at
+// their spectrum positions, written by bins_inv_kernel) + a short overflow list for the few positions where two
+// bins of one plane overlap.  u = IRFFT(plane 0 + plane 1 + overflow), overlap-added straight into y:
+// y[(k-1)*hop + p] += u_k[p].  Every output sample is the sum of exactly two slices, one even and one odd: the
+// launch with parity 0 STORES the even slices, the launch with parity 1 (stream-ordered after it) ADDS the odd ones
+// with fire-and-forget reductions (red.global.add: every location receives exactly one addition, so no ordering
+// question arises) -- no intermediate slice buffer, and a two-term sum is order independent (bitwise reproducible).
+// (reference: nsgt/nsigtf.py:82-103, nsgt/unslicing.py:33-69, nsgt/slicq.py:207-230)
 template <class PF>
 __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(const __grid_constant__ SlicqSliceParams p) {
     SLICQ_DYN_SMEM(float2, Z);
-    constexpr int N = PF::N;
+    constexpr int N = PF::N, NT = SLICQ_SLICE_THREADS, P3 = PF::P3, C3 = PF::C3;
     // CTA i of the launch = i-th slice of this launch's parity at or after unit rs0
     const int pi = p.par_base + blockIdx.x;
     const int row = pi / p.par_cs, k = 2 * (pi - row * p.par_cs) + p.parity;
     const int rsl = row * p.S + k - p.rs0;
-    PHASE_MARK(0);
-    // ---- gather of the windowed bin spectra + Hermitian pre-processing.
-    // Spectrum position f is the sum over the bins j = jlo .. jlo + n (n <= 3) covering it of
-    // T[f + gd[j]], always in the order (T_jlo + T_jlo+1) + (T_jlo+2 + T_jlo+3): deterministic.
-    // Under load a dependent global access costs a full L2/HBM round trip (~1000 cycles), so the phase
-    // is organised in as few round trips as possible:
-    //   1. tables: gd -> shared memory, this thread's NW pair descriptors and its "extra" entry -> registers
-    //   2. the rare third/fourth terms (gx list, < 5 % of the positions) are summed into Z / RN,
-    //      overlapped with the loads of round 0
-    //   3. NW / UG rounds: the first two terms of UG pairs (k, N-k) and their twiddle in flight together
-    int* gd = reinterpret_cast<int*>(Z + ((PF::SMEM_ELEMS + 1) & ~1));
-    float2* RN = reinterpret_cast<float2*>(gd + ((p.t.n_bins + 4 + 3) & ~3));
     const int tid = threadIdx.x;
-    constexpr int NT = SLICQ_SLICE_THREADS, NW = (N / 2 + NT) / NT, UG = SLICQ_GATHER_UG, NR = (NW + UG - 1) / UG;
-#ifdef SLICQ_DEBUG_TWRAP
-    const float2* __restrict__ Trow = p.spec + (long long)(rsl % SLICQ_DEBUG_TWRAP) * p.spec_stride;   // tuning experiment, see slicq_fft_tile.cuh
-#else
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
-#endif
-    for (int j = tid; j < p.t.n_bins + 4; j += NT) gd[j] = j < p.t.n_bins ? __ldg(p.t.gd + j) : 0;   // 4 pad entries
-    unsigned dsc[NR * UG];
+    // ---- R[f] = plane0[f] + plane1[f], f in [0, N]: ONE memory round trip for the whole row.  Plane 0 goes
+    // straight into Z (cp.async, 16 bytes = two positions per copy; rows are 16-byte aligned), plane 1 into
+    // registers; every thread then adds its own chunks (no barrier between the copy and the add).  The overflow
+    // entry of the thread (positions covered twice inside one plane) travels in the same round.
+    if (!(SLICQ_DBG_SKIP & 1)) {
+    constexpr int NV = N / 2 + 1, NR = (NV + NT - 1) / NT;   // 16-byte chunks (the last holds f = N and one pad), chunks per thread
+    {
+        const float4* __restrict__ q0 = reinterpret_cast<const float4*>(Trow + p.t.pl_off);
+        const float4* __restrict__ q1 = reinterpret_cast<const float4*>(Trow + p.t.pl_off + p.t.pl_len);
+        float4* Z4 = reinterpret_cast<float4*>(Z);
 #pragma unroll
-    for (int u = 0; u < NR * UG; ++u) {
-        const int kk = tid + u * NT;
-        dsc[u] = (kk <= N / 2) ? __ldg(p.t.gjp + kk) : 0u;
-    }
-    const int nx = p.t.n_gx;
-    int4 xe = make_int4(-1, 0, -1, 0);
-    if (tid < nx) xe = __ldg(p.t.gx + tid);
-    __syncthreads();
-    float2 a[UG][4], w[UG];
-    const typename PF::Walk wk0 = PF::walk_in(tid);
-    auto load_round = [&](int r) {
-#pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int kk = tid + (r * UG + u) * NT;
-            if (kk > N / 2) continue;
-            const unsigned d = dsc[r * UG + u];
-            const int* dk = gd + (d & 0x3fffu);
-            const int* dn = gd + ((d >> 16) & 0x3fffu);
-            a[u][0] = __ldg(Trow + kk + dk[0]);
-            if (((d >> 14) & 3u) >= 1u) a[u][1] = __ldg(Trow + kk + dk[1]);
-            a[u][2] = __ldg(Trow + (N - kk) + dn[0]);
-            if ((d >> 30) >= 1u) a[u][3] = __ldg(Trow + (N - kk) + dn[1]);
-            w[u] = __ldg(p.t.post_tw + kk);
+        for (int u = 0; u < NR; ++u) {
+            const int i = tid + u * NT;
+            if (i < NV) cp_async16(Z4 + i, q0 + i);
         }
-    };
-    auto consume_round = [&](int r) {
+        cp_async_commit();
+        float4 b[NR];
 #pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int kk = tid + (r * UG + u) * NT;
-            if (kk > N / 2) continue;
-            const unsigned d = dsc[r * UG + u];
-            const unsigned nk = (d >> 14) & 3u, nn = d >> 30;
-            const typename PF::Walk wkk = PF::step_in(wk0, (r * UG + u) * NT);
-            const int pk = PF::slot(wkk), pn = PF::slot(PF::neg(wkk));      // slots of kk and N - kk (kk = 0: both slot 0)
-            float2 rk = a[u][0], rn = a[u][2];
-            if (nk >= 1u) { rk.x += a[u][1].x; rk.y += a[u][1].y; }
-            if (nn >= 1u) { rn.x += a[u][3].x; rn.y += a[u][3].y; }
-            if (nk >= 2u) { const float2 e = Z[pk]; rk.x += e.x; rk.y += e.y; }
-            if (nn >= 2u) { const float2 e = (kk == 0) ? *RN : Z[pn]; rn.x += e.x; rn.y += e.y; }
-            if (kk == 0) {
-                // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
-                Z[pk] = make_float2(rk.x + rn.x, rk.x - rn.x);
-            } else {
-                const float2 E = make_float2(rk.x + rn.x, rk.y - rn.y);   // rk + conj(rn)
-                const float2 O = make_float2(rk.x - rn.x, rk.y + rn.y);   // rk - conj(rn)
-                const float2 t = cmul_conj(O, w[u]);                      // conj(w^k) O
-                Z[pk] = make_float2(E.x - t.y, E.y + t.x);       // E + i t
-                Z[pn] = make_float2(E.x + t.y, t.x - E.y);       // conj(E - i t)
+        for (int u = 0; u < NR; ++u) {
+            const int i = tid + u * NT;
+            if (i < NV) b[u] = __ldg(q1 + i);
+        }
+        int4 xe = make_int4(-1, 0, -1, 0);
+        if (tid < p.t.n_ex) xe = __ldg(p.t.ex + tid);
+        float2 x2 = make_float2(0.f, 0.f), x3 = make_float2(0.f, 0.f);
+        if (xe.x >= 0) { x2 = __ldg(Trow + xe.y); if (xe.z >= 0) x3 = __ldg(Trow + xe.z); }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+            const int i = tid + u * NT;
+            if (i < NV) {
+                const float4 a = Z4[i];
+                Z4[i] = make_float4(a.x + b[u].x, a.y + b[u].y, a.z + b[u].z, a.w + b[u].w);
             }
         }
-    };
-    // extras of this thread (entry tid of gx; lists longer than the CTA are finished below)
-    float2 x2 = make_float2(0.f, 0.f), x3 = make_float2(0.f, 0.f);
-    if (xe.x >= 0) { x2 = __ldg(Trow + xe.y); if (xe.z >= 0) x3 = __ldg(Trow + xe.z); }
-    load_round(0);
-    if (xe.x >= 0) {
-        const float2 e = make_float2(x2.x + x3.x, x2.y + x3.y);
-        if (xe.x < N) Z[PF::pos_in(xe.x)] = e; else *RN = e;
+        __syncthreads();
+        // overflow entries: position f also receives T[off0] (+ T[off1]); entries have distinct f
+        if (xe.x >= 0) { Z[xe.x].x += x2.x + x3.x; Z[xe.x].y += x2.y + x3.y; }
+        for (int i = tid + NT; i < p.t.n_ex; i += NT) {
+            const int4 q = __ldg(p.t.ex + i);
+            float2 e = __ldg(Trow + q.y);
+            if (q.z >= 0) { const float2 v = __ldg(Trow + q.z); e.x += v.x; e.y += v.y; }
+            Z[q.x].x += e.x; Z[q.x].y += e.y;
+        }
     }
-    for (int i = tid + NT; i < nx; i += NT) {
-        const int4 q = __ldg(p.t.gx + i);
-        float2 e = __ldg(Trow + q.y);
-        if (q.z >= 0) { const float2 v = __ldg(Trow + q.z); e.x += v.x; e.y += v.y; }
-        if (q.x < N) Z[PF::pos_in(q.x)] = e; else *RN = e;
-    }
-    __syncthreads();
+    // ---- Hermitian pre-processing, in place: Z[k] = E + i conj(w^k) O, Z[N-k] = conj(E - i conj(w^k) O)
+    {
+        constexpr int NP2 = (N / 2 + NT) / NT;      // pairs (k, N-k) per thread
+        float2 wk[NP2];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        consume_round(r);
-        if (r + 1 < NR) load_round(r + 1);
+        for (int u = 0; u < NP2; ++u) {
+            const int kk = tid + u * NT;
+            if (kk <= N / 2) wk[u] = __ldg(p.t.post_tw + kk);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NP2; ++u) {
+            const int kk = tid + u * NT;
+            if (kk > N / 2) continue;
+            const cpx rk = cpx_ld(Z + kk);
+            const cpx rn = cpx_ld(Z + N - kk);
+            if (kk == 0) {
+                // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
+                const float a = cpx_re(rk), b = cpx_re(rn);
+                Z[0] = make_float2(a + b, a - b);
+            } else {
+                const cpx E = caddc(rk, rn);                 // rk + conj(rn)
+                const cpx O = csubc(rk, rn);                 // rk - conj(rn)
+                const cpx t = cmulwc(O, wk[u]);              // conj(w^k) O
+                cpx_st(Z + kk, caddi(E, t));                 // E + i t
+                cpx_st(Z + N - kk, cconjp(csubi(E, t)));     // conj(E - i t)
+            }
+        }
+    }
     }
     __syncthreads();
-    PHASE_MARK(1);
-    pfa_passes<PF, true>(Z);
-    PHASE_MARK(5);
-    const float scale = 1.0f / (float)(2 * N);
-    // slice sample p = 2n, 2n+1 goes to y index tb + p;  first half (n < N/2) = hop k-1, second = hop k
+    if (!(SLICQ_DBG_SKIP & 2)) pass_a<PF, true, ColNat<PF>, ColL2<PF> >(Z);
+    if (!(SLICQ_DBG_SKIP & 4)) pass_b<PF, true>(Z);
+    // ---- pass C (last): thread t owns the orbit {t + C3 j} of the OUTPUT; element j has i3 = (t + j) mod P3.  The
+    // outputs go back to Z in natural order (all tasks of a thread stay in registers until every thread has read its
+    // inputs), and leave with coalesced stores / reductions.
+    {
+        constexpr int NRC = (C3 + NT - 1) / NT;
+        cpx v[NRC][P3];
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) {
+            const int t = tid + r * NT;
+            if (t < C3) {
+                const float2* src = Z + (t % PF::P1) * PF::SA + (t % PF::P2) * PF::SB;
+#pragma unroll
+                for (int c = 0; c < P3; ++c) v[r][c] = cpx_ld(src + c);
+                dft<P3, true>(v[r]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) {
+            const int t = tid + r * NT;
+            if (t < C3) {
+                const int s = t % P3;
+                const int j0 = s ? P3 - s : 0, w = P3 - j0;
+                float2* za = Z + t + j0 * C3;
+                float2* zb = za - N;
+#pragma unroll
+                for (int c = 0; c < P3; ++c) cpx_st((c >= w ? zb : za) + c * C3, v[r][c]);
+            }
+        }
+    }
+    __syncthreads();
+    // slice sample pair n = (2n, 2n+1) goes to y index tb + 2n;  first half (n < N/2) = hop k-1, second half = hop k
     const long long tb = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;
     float* __restrict__ yr = p.x + row * p.x_row_stride;
     const bool accumulate = p.parity != 0;
@@ -390,36 +362,37 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const bool first_to_halo = (k == 0);      // hop -1: other shard (halo) or before the signal (dropped)
     float* __restrict__ halo = (p.halo_out != nullptr && p.k0 > 0) ? p.halo_out + (long long)row * p.t.hop : nullptr;
     const bool vec = ((reinterpret_cast<uintptr_t>(yr + tb) & 7) == 0) && tb >= 0 && tb + 2 * N <= p.T && !first_to_halo;
-    // The odd slices add into hops an even slice has stored (previous launch): reductions
-    // (red.global.add, no return value) instead of load + add + store, so that this phase has no
-    // global round trip.  y = even + odd either way: bitwise the same two-term sum.
-    typename PF::Walk wo = PF::walk_out(threadIdx.x);
-    if (vec) {
-        const bool add1 = accumulate, add2 = accumulate && !second_store;
-        float* __restrict__ yo = yr + tb;
-        for (int n = threadIdx.x; n < N; n += SLICQ_SLICE_THREADS) {
-            const float2 z0 = Z[PF::slot(wo)];
-            wo = PF::step_out(wo, SLICQ_SLICE_THREADS);
-            const float2 z = make_float2(z0.x * scale, z0.y * scale);
-            if ((n < N / 2) ? add1 : add2) slicq_red_add2(yo + 2 * n, z); else *reinterpret_cast<float2*>(yo + 2 * n) = z;
+    const bool add1 = accumulate, add2 = accumulate && !second_store;
+    if (SLICQ_DBG_SKIP & 8) return;
+    if (vec && add1 == add2) {
+        float2* __restrict__ y2 = reinterpret_cast<float2*>(yr + tb);
+        constexpr int U = 7;
+        for (int n0 = tid; n0 < N; n0 += U * NT) {
+            cpx z[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (n0 + u * NT < N) z[u] = cpx_ld(Z + n0 + u * NT);
+            if (add1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (n0 + u * NT < N) slicq_red_add2(reinterpret_cast<float*>(y2 + n0 + u * NT), cpx_to(z[u]));
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (n0 + u * NT < N) cpx_st(y2 + n0 + u * NT, z[u]);
+            }
         }
     } else {
-        for (int n = threadIdx.x; n < N; n += SLICQ_SLICE_THREADS) {
-            const float2 z0 = Z[PF::slot(wo)];
-            wo = PF::step_out(wo, SLICQ_SLICE_THREADS);
-            const float2 z = make_float2(z0.x * scale, z0.y * scale);
+        for (int n = tid; n < N; n += NT) {
+            const float2 z = Z[n];
             const bool first = n < N / 2;
-            const bool add = accumulate && (first || !second_store);
+            const bool add = first ? add1 : add2;
             if (first && first_to_halo) {
                 if (halo) { halo[2 * n] = z.x; halo[2 * n + 1] = z.y; }
             } else {
-                const long long t = tb + 2 * n;
-                if (t >= 0 && t < p.T) { if (add) slicq_red_add(yr + t, z.x); else yr[t] = z.x; }
-                if (t + 1 >= 0 && t + 1 < p.T) { if (add) slicq_red_add(yr + t + 1, z.y); else yr[t + 1] = z.y; }
+                const long long ty = tb + 2 * n;
+                if (ty >= 0 && ty < p.T) { if (add) slicq_red_add(yr + ty, z.x); else yr[ty] = z.x; }
+                if (ty + 1 >= 0 && ty + 1 < p.T) { if (add) slicq_red_add(yr + ty + 1, z.y); else yr[ty + 1] = z.y; }
             }
         }
     }
-    PHASE_MARK(6);
 }
 
 // host-side helpers / launchers ---------------------------------------------------------------
@@ -428,20 +401,25 @@ extern "C" int slicq_slice_smem_bytes(int L) {
     return -1;
 }
 
-// dynamic shared memory of slice_fft_inv_kernel: Z, per-bin gather offsets (+ 4 pad entries), Nyquist value
-static int slice_inv_smem_bytes(const SlicqDeviceTables& t) {
-    size_t b = (size_t)((Pfa9030::SMEM_ELEMS + 1) & ~1) * sizeof(float2);
-    b += (size_t)((t.n_bins + 4 + 3) & ~3) * sizeof(int);
-    b += 2 * sizeof(float2);
-    return (int)b;
+// cudaFuncSetAttribute is per device: remember which devices have the opt-in for > 48 KB dynamic shared memory
+static int slice_attr(int smem) {
+#ifndef SLICQ_EMU
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    if (SLICQ_SET_SMEM(slice_fft_fwd_kernel<Pfa9030>, smem) != cudaSuccess) return -1;
+    if (SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64) done[dev] = true;
+#endif
+    return 0;
 }
 
 extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
     if (p->t.L != 2 * Pfa9030::N) return -2;
     const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
-    static int attr_done = 0;
-    if (!attr_done) { SLICQ_SET_SMEM(slice_fft_fwd_kernel<Pfa9030>, smem); attr_done = 1; }
+    if (slice_attr(smem)) return -3;
     SLICQ_LAUNCH(slice_fft_fwd_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
     return (int)cudaGetLastError();
 }
@@ -449,9 +427,8 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
     if (p->t.L != 2 * Pfa9030::N) return -2;
-    const int smem = slice_inv_smem_bytes(p->t);
-    static int attr_done = 0;
-    if (attr_done < smem) { SLICQ_SET_SMEM(slice_fft_inv_kernel<Pfa9030>, smem); attr_done = smem; }
+    const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
+    if (slice_attr(smem)) return -3;
     // slices of parity q among units [0, u) of rows of S slices
     const int S = p->S, q = p->parity, cs = (S + 1 - q) / 2;
     auto count = [&](long long u) { return (u / S) * cs + ((u % S) + 1 - q) / 2; };
@@ -462,4 +439,3 @@ extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s)
     SLICQ_LAUNCH(slice_fft_inv_kernel<Pfa9030>, dim3((unsigned)(c1 - c0)), dim3(SLICQ_SLICE_THREADS), smem, s, sp);
     return (int)cudaGetLastError();
 }
-

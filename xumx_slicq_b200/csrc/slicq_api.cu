@@ -1,9 +1,9 @@
 // C-ABI of libslicq (include/slicq.h): plan construction and the chunked launch sequences.
 //
 // forward  : per chunk of (row,slice) units   slice_fft_fwd_kernel -> bins_fwd_kernel
-// inverse  : per chunk                         bins_inv_kernel -> slice_fft_inv_kernel -> overlap_add_kernel
-// A chunk's intermediate spectra live in the caller-provided scratch buffer, sized so that it
-// stays resident in the 126 MB L2 (the spectra never make a round trip to HBM).
+// inverse  : per chunk                         bins_inv_kernel -> slice_fft_inv_kernel (even slices, then odd slices)
+// A chunk's intermediate spectra (analysis: padded half spectra H; synthesis: the two bin planes T) live in the
+// caller-provided scratch buffer; SLICQ_CHUNK_MB bounds the chunk (default: one chunk per call).
 #include "slicq_common.cuh"
 #include "../../include/slicq.h"
 
@@ -120,6 +120,7 @@ int fft_threads_per_transform(const FftPlan& f) {
 
 struct Bucket {
     int M, first_bin, n_bins, gt, tw_off, kind, A, B, smem_per_fft;
+    int gap_first, gap_n;   // entries of the gap list (zero-filled positions of T) this bucket owns
     double cost;     // relative work per unit (for the job split)
 };
 
@@ -144,6 +145,7 @@ struct slicq_plan {
     int bins_smem;        // dynamic shared memory of the bins kernels
     int pad_l, pad_r;
     long long spec_stride_fwd;
+    long long t_stride;   // complex elements per unit of the synthesis intermediate T
     long long chunk_bytes;
     int target_jobs;      // CTAs per bins launch the job split aims for
     int min_iters;        // ... but a job keeps at least this many iterations (instruction-cache reuse)
@@ -241,7 +243,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         Bucket b;
         b.M = p->bin_M[j]; b.first_bin = j; b.n_bins = 1; b.tw_off = tw_off;
         b.kind = f->kind; b.A = f->A; b.B = f->B; b.smem_per_fft = fft_smem_per_transform(*f);
-        b.gt = 1; b.cost = 0.0;
+        b.gt = 1; b.cost = 0.0; b.gap_first = 0; b.gap_n = 0;
         tw_off += b.M;
         p->buckets.push_back(b);
     }
@@ -264,7 +266,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         b.gt = gt;
         // + SLICQ_SLOT_BYTES; single-thread transforms keep the bucket's windows behind the stage
         // two-pass and prime transforms keep the job's twiddles (M complex) and dual windows (F * M floats) there too
-        const int sm = b.n_bins * gt * b.smem_per_fft + 4096 + (f->kind == 1 ? b.n_bins * b.M * 4 + 16 : 0) +
+        const int sm = b.n_bins * gt * b.smem_per_fft + 4096 + (f->kind == 1 ? b.n_bins * b.M * 4 + b.n_bins * 12 + 32 : 0) + (f->kind == 3 ? b.n_bins * 12 + 16 : 0) +
                        (f->kind >= 2 ? b.M * 8 + b.n_bins * b.M * 4 + b.n_bins * 4 + 16 : 0);
         if (sm > p->bins_smem) p->bins_smem = sm;
         // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
@@ -280,7 +282,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         for (int mc = 0; mc < M; ++mc) {            // centred order m' = m~ + M/2
             const int m = (mc + M / 2) % M;         // reference order (peak at m = 0)
             wf[o + mc] = (float)((double)t->win_fwd[o + m] * sgn / (double)M);
-            wi[o + mc] = (float)((double)t->win_inv[o + m] * sgn * (double)M);
+            wi[o + mc] = (float)((double)t->win_inv[o + m] * sgn * (double)M / (double)L);   // 1/L of the slice IFFT folded in
         }
         pad_l = std::max(pad_l, M / 2 - p->bin_pos[j]);
         pad_r = std::max(pad_r, p->bin_pos[j] + M / 2 - 1 - p->N2);
@@ -305,37 +307,73 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
             const double a = -2.0 * M_PI * (double)j / (double)b.M;
             tw[b.tw_off + j] = make_float2((float)cos(a), (float)sin(a));
         }
-    // synthesis gather tables (slice_fft_inv_kernel): the bins covering a position are consecutive,
-    // bin j contributes T[f + gd[j]]; positions are scheduled by the chunk of T their last term lies in
-    std::vector<int> gd(J);
-    for (int j = 0; j < J; ++j) gd[j] = p->bin_coff[j] - p->bin_pos[j] + p->bin_M[j] / 2;
-    std::vector<unsigned> gj(p->N2 + 1);
-    std::vector<int4> gx;
-    if (J >= (1 << 14)) { delete p; return fail(SLICQ_E_UNSUPPORTED, "too many bins for the gather descriptors"); }
-    for (int f = 0; f <= p->N2; ++f) {
-        int jlo = -1, jhi = -1, n = 0;
-        for (int j = 0; j < J; ++j) {
-            const int d = f - p->bin_pos[j], h = p->bin_M[j] / 2;
-            if (d >= -h && d < h) {
-                if (jlo < 0) jlo = j;
-                jhi = j;
-                ++n;
+    // synthesis intermediate T (see SlicqDeviceTables): two planes + overflow + gap list
+    const int N2 = p->N2;
+    const int pl_off = pad_l;                                            // even
+    const int pl_len = (pl_off + N2 + 2 + std::max(pad_r, 2) + 1) & ~1;  // positions -pl_off .. N2 + 1 + pad_r, even
+    std::vector<int> toff(J), ov(J, 0), ovoff(J, 0);
+    int n_ovf = 0;
+    for (int j = 0; j < J; ++j) {
+        const int lo = p->bin_pos[j] - p->bin_M[j] / 2;
+        toff[j] = (j & 1) * pl_len + pl_off + lo;
+        if (j >= 2) {
+            const int end_prev = p->bin_pos[j - 2] + p->bin_M[j - 2] / 2;
+            ov[j] = std::max(0, end_prev - lo);
+        }
+        if (ov[j] > p->bin_M[j] || (ov[j] & 1)) { delete p; return fail(SLICQ_E_UNSUPPORTED, "unsupported overlap between bins of one plane"); }
+        if (j >= 4 && p->bin_pos[j - 4] + p->bin_M[j - 4] / 2 > lo) { delete p; return fail(SLICQ_E_UNSUPPORTED, "more than 4 bins overlap at one spectrum position"); }
+        ovoff[j] = 2 * pl_len + n_ovf;
+        n_ovf += ov[j];
+    }
+    // two-pass / prime transforms store their first run of A outputs through one select: the overflow part must fit
+    for (const Bucket& b : p->buckets)
+        for (int j = b.first_bin; j < b.first_bin + b.n_bins; ++j)
+            if (b.kind != 1 && ov[j] > b.A) { delete p; return fail(SLICQ_E_UNSUPPORTED, "overlap between bins of one plane exceeds the first transform pass"); }
+    p->t_stride = (2LL * pl_len + n_ovf + 1) & ~1LL;
+    std::vector<int4> ex;
+    {
+        std::vector<int> e0(N2 + 1, -1), e1(N2 + 1, -1);
+        for (int j = 0; j < J; ++j)
+            for (int m = 0; m < ov[j]; ++m) {
+                const int f = p->bin_pos[j] - p->bin_M[j] / 2 + m;
+                if (f < 0 || f > N2) continue;
+                if (e0[f] < 0) e0[f] = ovoff[j] + m; else e1[f] = ovoff[j] + m;
+            }
+        for (int f = 0; f <= N2; ++f)
+            if (e0[f] >= 0) ex.push_back(int4{f, e0[f], e1[f], 0});
+    }
+    const int n_ex = (int)ex.size();
+    if (ex.empty()) ex.push_back(int4{0, 0, -1, 0});
+    // gaps: positions 0 .. N2 + 1 of a plane that none of its bins covers; owner = the next bin of the plane (or its last)
+    std::vector<int2> gaps;
+    {
+        std::vector<std::vector<int2> > per_bucket(p->buckets.size());
+        auto bucket_of = [&](int j) { for (size_t i = 0; i < p->buckets.size(); ++i) if (j >= p->buckets[i].first_bin && j < p->buckets[i].first_bin + p->buckets[i].n_bins) return (int)i; return 0; };
+        for (int q = 0; q < 2; ++q) {
+            std::vector<int> owner(N2 + 2, -1);    // covering bin or -1
+            int last = -1;
+            for (int j = q; j < J; j += 2) {
+                const int lo = std::max(0, p->bin_pos[j] - p->bin_M[j] / 2), hi = std::min(N2 + 2, p->bin_pos[j] + p->bin_M[j] / 2);
+                for (int f = lo; f < hi; ++f) owner[f] = j;
+                last = j;
+            }
+            if (last < 0) { delete p; return fail(SLICQ_E_UNSUPPORTED, "a bin plane is empty"); }
+            for (int f = 0; f < N2 + 2;) {
+                if (owner[f] >= 0) { ++f; continue; }
+                int g = f;
+                while (g < N2 + 2 && owner[g] < 0) ++g;
+                const int next = g < N2 + 2 ? owner[g] : last;
+                per_bucket[bucket_of(next)].push_back(int2{q * pl_len + pl_off + f, g - f});
+                f = g;
             }
         }
-        if (n == 0) { delete p; return fail(SLICQ_E_UNSUPPORTED, "spectrum position not covered by any bin"); }
-        if (n > 4) { delete p; return fail(SLICQ_E_UNSUPPORTED, "more than 4 bins overlap at one spectrum position"); }
-        if (jhi - jlo + 1 != n) { delete p; return fail(SLICQ_E_UNSUPPORTED, "bins covering a spectrum position are not consecutive"); }
-        gj[f] = (unsigned)(jlo | ((n - 1) << 14));
-        if (n >= 3) {
-            int4 e;
-            e.x = f; e.y = f + gd[jlo + 2]; e.z = (n == 4) ? f + gd[jlo + 3] : -1; e.w = 0;
-            gx.push_back(e);
+        for (size_t i = 0; i < p->buckets.size(); ++i) {
+            p->buckets[i].gap_first = (int)gaps.size();
+            p->buckets[i].gap_n = (int)per_bucket[i].size();
+            gaps.insert(gaps.end(), per_bucket[i].begin(), per_bucket[i].end());
         }
     }
-    std::vector<unsigned> gjp(p->N2 / 2 + 1);
-    for (int k = 0; k <= p->N2 / 2; ++k) gjp[k] = gj[k] | (gj[p->N2 - k] << 16);
-    const int n_gx = (int)gx.size();
-    if (gx.empty()) gx.push_back(int4{-1, 0, -1, 0});
+    if (gaps.empty()) gaps.push_back(int2{0, 0});
     SlicqDeviceTables& d = p->dev;
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
@@ -352,10 +390,12 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(p->bin_coff, &d.bin_coff, p->owned);
     rc |= upload(post, &d.post_tw, p->owned);
     rc |= upload(tw, &d.tw, p->owned);
-    rc |= upload(gjp, &d.gjp, p->owned);
-    rc |= upload(gd, &d.gd, p->owned);
-    rc |= upload(gx, &d.gx, p->owned);
-    d.n_gx = n_gx;
+    rc |= upload(toff, &d.bin_toff, p->owned);
+    rc |= upload(ov, &d.bin_ov, p->owned);
+    rc |= upload(ovoff, &d.bin_ovoff, p->owned);
+    rc |= upload(ex, &d.ex, p->owned);
+    rc |= upload(gaps, &d.gaps, p->owned);
+    d.n_ex = n_ex; d.pl_off = pl_off; d.pl_len = pl_len; d.t_stride = (int)p->t_stride;
     if (rc) {
         slicq_plan_destroy(p);
         return fail(SLICQ_E_CUDA, "device table upload failed");
@@ -407,7 +447,7 @@ extern "C" int64_t slicq_plan_num_slices(const slicq_plan* p, int64_t T) {
 namespace {
 long long bytes_per_unit(const slicq_plan* p, int inverse) {
     if (!inverse) return p->spec_stride_fwd * 8;
-    return (long long)p->sum_M * 8;
+    return p->t_stride * 8;
 }
 long long chunk_units(const slicq_plan* p, int inverse) {
     long long c = p->chunk_bytes / bytes_per_unit(p, inverse);
@@ -466,6 +506,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
         a.ptr = reinterpret_cast<float2*>(views[i].ptr);
         a.s_row = views[i].s_row; a.s_bin = views[i].s_bin; a.s_slice = views[i].s_slice;
         a.M = b.M; a.first_bin = b.first_bin; a.n_bins = b.n_bins; a.gt = b.gt; a.tw_off = b.tw_off;
+        a.gap_first = b.gap_first; a.gap_n = b.gap_n;
         a.mptr = masks ? reinterpret_cast<const float*>(masks[i].ptr) : nullptr;
         a.nptr = norms ? reinterpret_cast<float*>(norms[i].ptr) : nullptr;
         const slicq_bucket_view* aux = masks ? masks : norms;      // synthesis masks or analysis magnitudes: never both
@@ -675,11 +716,11 @@ int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const sli
     float2* T = reinterpret_cast<float2*>(base);
     (void)nu;
     SlicqBinsParams* bp = new SlicqBinsParams();
-    bp->t = p->dev; bp->spec = T; bp->spec_stride = p->sum_M; bp->S = (int)n_slices;
+    bp->t = p->dev; bp->spec = T; bp->spec_stride = p->t_stride; bp->S = (int)n_slices;
     bp->x_rows = masks ? (int)x_rows : 0;
     SlicqSliceParams sp;
     memset(&sp, 0, sizeof sp);
-    sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->sum_M; sp.S = (int)n_slices;
+    sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->t_stride; sp.S = (int)n_slices;
     sp.x = y; sp.x_row_stride = y_row_stride; sp.T = length; sp.t0 = t0; sp.halo_out = halo_out;
     int rc = 0;
     for (long long u0 = 0; u0 < units && rc == 0;) {

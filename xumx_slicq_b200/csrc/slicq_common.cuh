@@ -92,6 +92,25 @@ SLICQ_DEVFN void slicq_red_add2(float* p, float2 v) {   // p 8-byte aligned
 }
 #endif
 
+// ---------------------------------------------------------------------------------------
+// asynchronous global -> shared copies (cp.async / LDGSTS): the data lands in shared memory without passing
+// through registers, so a phase can have all of its loads in flight at once
+#ifdef SLICQ_EMU
+static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async8(void* d, const void* s) { memcpy(d, s, 8); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+#else
+SLICQ_DEVFN void cp_async16(void* d, const void* s) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s) : "memory");
+}
+SLICQ_DEVFN void cp_async8(void* d, const void* s) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s) : "memory");
+}
+SLICQ_DEVFN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> SLICQ_DEVFN void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 #define SLICQ_MAX_BUCKETS 96
 #define SLICQ_MAX_M 292
 
@@ -129,11 +148,18 @@ struct SlicqDeviceTables {
     const int* bin_coff;    // [J]  offset of bin j inside a packed [sum_M] row
     const float2* post_tw;  // [N2/2 + 1]  exp(-2 pi i k / L)
     const float2* tw;       // concatenated per-bucket twiddles exp(-2 pi i j / M_b), j in [0, M_b)
-    // synthesis gather: spectrum position f is the sum over bins j = jlo .. jlo + n of T[f + gd[j]]
-    const unsigned* gjp;          // [N2/2 + 1] descriptor of the pair (k, N2 - k): (jlo | n << 14) of k, << 16 the same for N2 - k
-    const int* gd;                // [J]       coff_j - pos_j + M_j / 2
-    const int4* gx;               // [n_gx]    positions covered by 3 or 4 bins: {f, offset of the 3rd term, of the 4th or -1, 0}
-    int n_gx;
+    // synthesis intermediate T, one row per unit: [plane 0][plane 1][overflow].  Plane q holds the windowed spectra
+    // of the bins j with j % 2 == q at their spectrum positions (index pl_off + f); where two bins of one plane
+    // overlap (a few positions) the leading part of the later bin goes to the overflow area instead, and the
+    // few positions no bin of a plane covers ("gaps") are zero-filled by the bins kernel.
+    int pl_off, pl_len;           // plane q starts at q * pl_len; position f sits at q * pl_len + pl_off + f  (both even)
+    int t_stride;                 // complex elements per row of T (even)
+    const int* bin_toff;          // [J] offset in the row of coefficient m' = 0 of bin j
+    const int* bin_ov;            // [J] leading coefficients of bin j that go to the overflow area (even, usually 0)
+    const int* bin_ovoff;         // [J] offset in the row of the overflow slot of m' = 0
+    const int4* ex;               // [n_ex] {f, off0, off1 or -1, 0}: position f also receives T[off0] (+ T[off1])
+    int n_ex;
+    const int2* gaps;             // {offset in the row, count}: zero-filled per unit by the job of the owning bucket
 };
 
 // one bucket as a kernel sees it for one call (pointer + strides of the caller's tensor)
@@ -150,6 +176,7 @@ struct SlicqBucketArg {
     int job_start;        // first job (CTA) index of this bucket inside the launch
     int n_jobs;           // CTAs working on this bucket
     int units_per_job;    // multiple of gt
+    int gap_first, gap_n;  // synthesis: entries of SlicqDeviceTables::gaps this bucket zero-fills
     // fused mask*mix synthesis (slicq_inverse_masked): fp32 mask of the same logical shape as the
     // OUTPUT rows [targets*rows][F][S][M]; null = plain synthesis
     const float* mptr;

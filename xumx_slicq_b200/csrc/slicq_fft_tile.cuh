@@ -163,10 +163,16 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
     long long* so = reinterpret_cast<long long*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
     float2* stage = sm + (gs * j.F + f) * PITCH;
-    // the bucket's dual windows (contiguous in wi, like the bins in T) live behind the stage and are
-    // applied on the way out: no per-thread window registers next to the M-point codelet
+    // the bucket's dual windows (contiguous in wi) and the T-row offsets of its bins live behind the stage; both
+    // are applied on the way out: no per-thread window registers next to the M-point codelet
     float* wsm = reinterpret_cast<float*>(sm + j.gt * j.F * PITCH);
+    int* tob = reinterpret_cast<int*>(wsm + FM);           // [F] {offset of m' = 0, overflow count, overflow offset}
     for (int t = tid; t < FM; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff0 + t);
+    for (int t = tid; t < j.F; t += blockDim.x) {
+        tob[3 * t] = __ldg(p.t.bin_toff + j.first_bin + t);
+        tob[3 * t + 1] = __ldg(p.t.bin_ov + j.first_bin + t);
+        tob[3 * t + 2] = __ldg(p.t.bin_ovoff + j.first_bin + t);
+    }
     const bool vec = b.mptr == nullptr && ((reinterpret_cast<uintptr_t>(b.ptr) & 15) == 0) &&
                      (((b.s_row | b.s_bin | b.s_slice) & 1) == 0);
     for (int base = j.u0; base < j.u1; base += j.gt) {
@@ -201,13 +207,14 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
             for (int m = 0; m < M; ++m) stage[m] = v[m];
         }
         __syncthreads();
-        // rows of T are 16-byte aligned and coff / M are even: two coefficients per store
+        // rows of T are 16-byte aligned, bin offsets / overflow counts are even: two coefficients per store
         for (int t = tid; t < ng * (FM / 2); t += blockDim.x) {
             const int g = t / (FM / 2), e = 2 * (t - g * (FM / 2));
             const int fb = e / M, n = e - fb * M;
             const float2* src = sm + (g * j.F + fb) * PITCH + n;
             const float w0 = wsm[e], w1 = wsm[e + 1];
-            *reinterpret_cast<float4*>(p.spec + SLICQ_TROW(base + g) * p.spec_stride + coff0 + e) =
+            const int off = (n < tob[3 * fb + 1] ? tob[3 * fb + 2] : tob[3 * fb]) + n;
+            *reinterpret_cast<float4*>(p.spec + SLICQ_TROW(base + g) * p.spec_stride + off) =
                 make_float4(src[0].x * w0, src[0].y * w0, src[1].x * w1, src[1].y * w1);
         }
     }
@@ -308,12 +315,14 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     const int f1 = r1 / B, n2 = r1 - f1 * B;
     const bool act1 = gs1 < j.gt;
     const bool odd = n2 & 1;
-    // per-slot constants of pass 2 (do not change over the job): unit offset gs and row offset coff_f
-    int2* sc = reinterpret_cast<int2*>(sm);
+    // per-slot constants of pass 2 (do not change over the job): unit offset gs | bin << 16, T-row offset of the bin,
+    // its overflow count and overflow offset (leading outputs of a bin that overlaps its plane neighbour)
+    int4* sc = reinterpret_cast<int4*>(sm);
     sm += SLICQ_SLOT_BYTES / sizeof(float2);
     for (int t = tid; t < j.gt * j.F; t += blockDim.x) {
         const int gs = t / j.F, f = t - gs * j.F;
-        sc[t] = make_int2(gs, __ldg(p.t.bin_coff + j.first_bin + f));
+        sc[t] = make_int4(gs | (f << 16), __ldg(p.t.bin_toff + j.first_bin + f), __ldg(p.t.bin_ov + j.first_bin + f),
+                          __ldg(p.t.bin_ovoff + j.first_bin + f));
     }
     float2* y1 = sm + (gs1 * j.F + f1) * PER + n2;
     // The job's twiddles, transposed to [k1][n2], and the bucket's dual windows live in shared memory
@@ -359,17 +368,23 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         for (int t = tid; t < ng * j.F * A; t += blockDim.x) {
             const int slot = t / A, k1 = t - slot * A;
-            const int2 c = sc[slot];
+            const int4 c = sc[slot];
             const float2* src = sm + slot * PER + k1 * BP;
             float2 v[B];
 #pragma unroll
             for (int n = 0; n < B; ++n) v[n] = src[n];
             dft<B, false>(v);
-            const int off = c.y + k1;
-            float2* o = p.spec + SLICQ_TROW(base + c.x) * p.spec_stride + off;
-            const float* wp = wsm + (off - coff_first);
+            float2* row = p.spec + SLICQ_TROW(base + (c.x & 0xffff)) * p.spec_stride;
+            float2* o = row + c.y + k1;
+            const float* wp = wsm + (c.x >> 16) * M + k1;
+            // overflow counts never exceed A (checked by slicq_plan_create): only output k2 = 0 can be diverted
+            {
+                const float w = wp[0];
+                float2* o0 = (k1 < c.z) ? row + c.w + k1 : o;
+                *o0 = make_float2(v[0].x * w, v[0].y * w);
+            }
 #pragma unroll
-            for (int k2 = 0; k2 < B; ++k2) {
+            for (int k2 = 1; k2 < B; ++k2) {
                 const float w = wp[A * k2];
                 o[A * k2] = make_float2(v[k2].x * w, v[k2].y * w);
             }
@@ -472,10 +487,16 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
     float* wsm = reinterpret_cast<float*>(twsm + M);
     const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
     const int FM = j.F * M;
+    int* tob = reinterpret_cast<int*>(wsm + FM);           // [F] {offset of m' = 0 in the T row, overflow count, overflow offset}
     {
         const float2* __restrict__ tw = p.t.tw + b.tw_off;
         for (int t = tid; t < M; t += blockDim.x) { const int k1 = t / P, c2 = t - k1 * P; twsm[t] = __ldg(tw + c2 * k1); }
         for (int t = tid; t < FM; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff_first + t);
+        for (int t = tid; t < j.F; t += blockDim.x) {
+            tob[3 * t] = __ldg(p.t.bin_toff + j.first_bin + t);
+            tob[3 * t + 1] = __ldg(p.t.bin_ov + j.first_bin + t);
+            tob[3 * t + 2] = __ldg(p.t.bin_ovoff + j.first_bin + t);
+        }
     }
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
@@ -533,7 +554,8 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
                     y.y -= br;
                 }
                 const float wv = wsm[e];
-                p.spec[SLICQ_TROW(base + gs) * p.spec_stride + coff_first + e] = make_float2(y.x * wv, y.y * wv);
+                const int off = (r < tob[3 * f + 1] ? tob[3 * f + 2] : tob[3 * f]) + r;
+                p.spec[SLICQ_TROW(base + gs) * p.spec_stride + off] = make_float2(y.x * wv, y.y * wv);
                 e += blockDim.x;
                 while (e >= FM) { e -= FM; ++gs; }
             }
