@@ -563,14 +563,18 @@ def choose_split(M: int):
         return (3, p, r)
     if M in COMPLEX_SIZES:
         return (1, M, 1)
+    # two passes A x B through shared memory: B even (the centring shift by M/2 becomes a rotation of pass 2),
+    # both factors register friendly; cost = packed instructions of the codelets + twiddle multiplications
     best = None
     for a in COMPLEX_SIZES:
-        if M % a:
+        if M % a or a > 23:
             continue
         b = M // a
-        if b not in COMPLEX_SIZES or b > a:
+        if b not in COMPLEX_SIZES or b % 2 or b > 20 or b < 4:
             continue
-        cost = codelet_flops(a) * b + codelet_flops(b) * a
+        cost = codelet_flops(a) * b + codelet_flops(b) * a + 2 * (a - 1) * (b - 1) + 3 * M
+        if a < b:          # pass 2 would run with idle threads (A tasks per transform against B in pass 1)
+            cost += 100000
         if best is None or cost < best[0]:
             best = (cost, a, b)
     assert best is not None, M
@@ -579,10 +583,18 @@ def choose_split(M: int):
 
 def generate_sizes() -> str:
     lines = ["// GENERATED by gen_codelets.py -- FFT plans per coefficient length M.",
-             "// SLICQ_FFT_SIZE(M, KIND, A, B): kind 1 single-thread, 2 two-pass AxB, 3 prime P=A times R=B"]
+             "// SLICQ_FFT_SIZE(M, KIND, A, B, COST): kind 1 single-thread, 2 two-pass AxB, 3 prime P=A times R=B;",
+             "// COST = instructions per transform of the tiled kernels (packed arithmetic + ~14 per element of data movement)"]
     for M in range(16, SLICQ_MAX_M + 1, 4):
         k, a, b = choose_split(M)
-        lines.append(f"SLICQ_FFT_SIZE({M}, {k}, {a}, {b})")
+        if k == 1:
+            cost = codelet_flops(M) + 12 * M
+        elif k == 2:
+            cost = codelet_flops(a) * b + codelet_flops(b) * a + 3 * M + 14 * M
+        else:
+            nparts = dict(PRIME_PARTS[1:])[a]
+            cost = b * sum(gen_prime_part(a, nparts, q, False)[1] + 2 * a for q in range(nparts)) + a * codelet_flops(b) + 3 * M + 14 * M
+        lines.append(f"SLICQ_FFT_SIZE({M}, {k}, {a}, {b}, {cost})")
     return "\n".join(lines) + "\n"
 
 

@@ -84,7 +84,7 @@ SLICQ_DEVFN void bins_body(const SlicqBinsParams& p, unsigned char* smem) {
         }
     }
     switch (b.M) {
-#define SLICQ_FFT_SIZE(M_, K_, A_, B_) \
+#define SLICQ_FFT_SIZE(M_, K_, A_, B_, C_) \
     case M_: JobRunner<M_, K_, A_, B_, SYNTH>::run(p, b, j, smem); break;
 #include "fft_sizes.inc"
 #undef SLICQ_FFT_SIZE

@@ -86,9 +86,9 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
-struct FftPlan { int M, kind, A, B; };
+struct FftPlan { int M, kind, A, B, cost; };
 const FftPlan kFftPlans[] = {
-#define SLICQ_FFT_SIZE(M_, K_, A_, B_) {M_, K_, A_, B_},
+#define SLICQ_FFT_SIZE(M_, K_, A_, B_, C_) {M_, K_, A_, B_, C_},
 #include "fft_sizes.inc"
 #undef SLICQ_FFT_SIZE
 };
@@ -270,7 +270,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
                        (f->kind >= 2 ? b.M * 8 + b.n_bins * b.M * 4 + b.n_bins * 4 + 16 : 0);
         if (sm > p->bins_smem) p->bins_smem = sm;
         // work model: flops ~ M log2 M per transform plus a per-coefficient load/store term
-        b.cost = (double)b.n_bins * b.M * (log2((double)b.M) + (f->kind == 3 ? 0.12 * f->A : 0.0) + 4.0);
+        b.cost = (double)b.n_bins * f->cost;   // instructions per transform (fft_sizes.inc)
     }
 
     // ---- derived tables
