@@ -104,31 +104,82 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
+def _import_reference():
+    """The UNMODIFIED reference package (xumx_slicq_v2): baseline/_ref (pip --target install),
+    then $SLICQ_REFERENCE, then /root/reference.  Returns (module transforms, where) or (None, why)."""
+    import importlib
+    cands = [os.path.join(ROOT, "baseline", "_ref"), os.environ.get("SLICQ_REFERENCE", ""), "/root/reference"]
+    why = "not found"
+    for c in cands:
+        if not c or not os.path.isdir(os.path.join(c, "xumx_slicq_v2")):
+            continue
+        sys.path.insert(0, c)
+        try:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mod = importlib.import_module("xumx_slicq_v2.transforms")
+            return mod, c
+        except Exception as e:          # missing optional dependency of the reference package
+            why = f"{c}: {type(e).__name__}: {e}"
+            sys.path.remove(c)
+    return None, why
+
+
 def cpu_reference_arm(steps: int, warmup: int, sample_seconds: float):
-    """The reference's algorithm on the host cores: the NumPy/pocketfft port in oracle/ (the
-    reference is pure Python/torch and cannot travel to the GPU box).  fp32 storage
-    like the reference, all host threads for the FFTs."""
-    from oracle.slicq_oracle import SlicqOracle
+    """The reference's own CPU implementation of the path on the host cores, all threads: the unmodified
+    xumx_slicq_v2 NSGT_SL / INSGT_SL (torch, device="cpu") when the package can be imported (kind "reference"),
+    else the NumPy/pocketfft port in oracle/ (kind "port").  One step = a bounded sample of the workload:
+    a `sample_seconds` stereo mixture, 1 forward + inverse of 4 targets.
+    Returns (audio-s/s, seconds per step, cores, sample description, kind)."""
     cores = os.cpu_count() or 1
-    orc = SlicqOracle(**SCALE, dtype=np.float32, workers=cores)
     Ts = int(sample_seconds * FS)
     rs = np.random.RandomState(0)
     x = (rs.rand(2, Ts).astype(np.float32) * 2 - 1)
+    sample = f"{sample_seconds:g} s stereo mixture: 1 forward (2 rows) + inverse of 4 targets (8 rows)"
+    ref, where = _import_reference()
+    if ref is not None:
+        import io, contextlib, warnings
+        import torch
+        torch.set_num_threads(cores)
+        with contextlib.redirect_stdout(io.StringIO()):
+            base = ref.NSGTBase(SCALE["scale"], SCALE["fbins"], SCALE["fmin"], device="cpu")
+        nsgt, insgt = ref.make_filterbanks(base)
+        xt = torch.from_numpy(x).view(1, 2, Ts)
+        gains = torch.tensor(GAINS).view(4, 1, 1, 1, 1, 1, 1)
 
-    def step():
-        C = orc.forward(x)
-        Y = [np.concatenate([c * np.float32(g) for g in GAINS], axis=1) for c in C]   # [S, 4*2, F, M]
-        return orc.backward(Y, Ts)
+        def step():
+            with torch.no_grad(), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                X = nsgt(xt)
+                # model-output stand-in (contiguous like Unmix outputs; the reference's backward mutates it: fresh every step)
+                Y = [(Xb.unsqueeze(0) * gains).contiguous() for Xb in X]
+                return insgt(Y, Ts)
+        kind = "reference"
+        sample += f"; unmodified xumx_slicq_v2 torch CPU path from {os.path.relpath(where, ROOT) if where.startswith(ROOT) else where}, {cores} threads"
+    else:
+        from oracle.slicq_oracle import SlicqOracle
+        orc = SlicqOracle(**SCALE, dtype=np.float32, workers=cores)
+
+        def step():
+            C = orc.forward(x)
+            Y = [np.concatenate([c * np.float32(g) for g in GAINS], axis=1) for c in C]   # [S, 4*2, F, M]
+            return orc.backward(Y, Ts)
+        kind = "port"
+        sample += f"; NumPy port (reference package not importable: {where})"
 
     for _ in range(max(1, warmup)):
         step()
     times = []
+    t_start = time.perf_counter()
     for _ in range(steps):
         t = time.perf_counter()
         step()
         times.append(time.perf_counter() - t)
+        if time.perf_counter() - t_start > 150.0:      # keep the arm within a few minutes on slow hosts
+            break
     dt = float(np.mean(times))
-    return sample_seconds / dt, dt, cores, f"{sample_seconds:g} s stereo mixture: 1 forward (2 rows) + inverse of 4 targets (8 rows)"
+    return sample_seconds / dt, dt, cores, sample, kind, len(times)
 
 
 def bench_slices(args, nsg, dev, rank, world, distributed):
@@ -192,6 +243,36 @@ def bench_slices(args, nsg, dev, rank, world, distributed):
         dist.destroy_process_group()
 
 
+def bind_rank_to_cores(local_rank: int, local_world: int):
+    """Pin this rank to its own share of the host cores near its GPU (NVML cpu affinity of the device, split evenly
+    between the ranks that share it), BEFORE pinned buffers are allocated: page-locked staging memory is then
+    first-touched on the GPU's NUMA node and the copy-submitting threads of the ranks do not migrate over each other.
+    Returns a description for the bench line."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1 and w * 64 + b < ncpu]
+        try:
+            numa = [w * 64 + b for w, m in enumerate(pynvml.nvmlDeviceGetMemoryAffinity(h, 4, 0)) for b in range(64) if (m >> b) & 1]
+        except Exception:
+            numa = None
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # ranks whose GPUs share this affinity mask split it evenly
+        per = max(1, len(allowed) // max(1, local_world))
+        mine = allowed[(local_rank % max(1, local_world)) * per:(local_rank % max(1, local_world) + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        info = {"bound": True, "cores": f"{mine[0]}-{mine[-1]}", "n_cores": len(mine), "gpu_numa_nodes": numa,
+                "gpu_cpu_affinity": f"{cpus[0]}-{cpus[-1]}" if cpus else None}
+    except Exception as e:                      # binding is an optimisation: report and carry on
+        info["error"] = f"{type(e).__name__}: {e}"[:160]
+    return info
+
+
 _JSON_FD = None
 
 
@@ -234,6 +315,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    binding = bind_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if args.impl != "reference" else None
     base_cfg = {"workload": "configs[1]: sliCQT path of a realtime demix of synthetic 30 s 44.1 kHz stereo mixtures "
                             "(per mixture: 1 forward of 2 rows x 148 slices + inverse of 4 targets = 8 rows x 148 slices), "
                             "Bark(262, 32.9 Hz), sllen 18060; one step = one batch of mixtures per GPU, as "
@@ -245,15 +327,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
-        steps = max(1, min(args.steps, 5))
-        val, dt, cores, sample = cpu_reference_arm(steps, min(args.warmup, 1), args.cpu_sample_seconds)
+        val, dt, cores, sample, kind, done = cpu_reference_arm(args.steps, args.warmup, args.cpu_sample_seconds)
         emit(({
             "impl": "reference", "metric": "sliCQT fwd+inv audio-sec/sec", "value": val, "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": base_cfg,
-            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }))
@@ -453,7 +533,35 @@ def main():
     if distributed:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_ms = float(te.item())
+    # ---- what the host side of this box allows: the same bytes per step as plain pinned copies (H2D and D2H on two
+    #      streams, no kernels), all ranks at once -- the ceiling of any end-to-end number at this N
+    yd_c = torch.empty(N_TARGETS, B, 2, T, dtype=torch.float32, device=dev)
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copies_only():
+        with torch.cuda.stream(s_h2d):
+            xh.to(dev, non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            yh.copy_(yd_c, non_blocking=True)
+    for _ in range(3):
+        copies_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        copies_only()
+    torch.cuda.synchronize(dev)
+    barrier()
+    c_ms = (time.perf_counter() - t0) / e_steps * 1e3
+    tc = torch.tensor([c_ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    c_ms = float(tc.item())
+    del yd_c
     e2e = {"value": audio_s / (e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e_ms,
+           "host_copy_ceiling": {"value": audio_s / (c_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": c_ms,
+                                 "what": "pinned H2D + D2H of the same byte counts on two streams, no kernels, all ranks concurrently",
+                                 "gbytes_per_s_per_gpu": round((xh.numel() + yh.numel()) * 4 / (c_ms * 1e-3) / 1e9, 1)},
+           "frac_of_host_copy_ceiling": round(c_ms / e_ms, 3), "host_binding": binding,
            "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4),
            "includes": "every step: pinned H2D of the mixtures, NSGT_SL, 4-target gain stand-in (torch), INSGT_SL, "
                        "pinned D2H of the 4 target waveforms; xumx_slicq_b200.pipeline.TransformStream overlaps the "
@@ -551,8 +659,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, sample = cpu_reference_arm(3, 1, args.cpu_sample_seconds)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample,
+        v, dt, cores, sample, kind, _ = cpu_reference_arm(5, 1, args.cpu_sample_seconds)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample,
                "ms_per_sample": dt * 1e3}
 
     if rank == 0:

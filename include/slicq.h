@@ -16,7 +16,10 @@
  *   - return value 0 = success, negative = SLICQ_E_* ; slicq_last_error() gives a thread-local
  *     human readable message.  No C++ exception crosses the boundary.
  *   - a plan is immutable after creation; calls on one plan are re-entrant across threads as
- *     long as they use distinct scratch buffers.
+ *     long as they use distinct scratch buffers (large calls fork onto the plan's internal side
+ *     streams: that enqueue sequence is serialised by a per-plan mutex, the GPU work is not).
+ *   - a plan belongs to the device that was current in slicq_plan_create; one process may hold
+ *     plans on several devices (kernel attributes are set per device).
  *   - "row"  = one flattened (batch x channel) signal,  "slice" = one 50 %-overlapping window of
  *     sl_len samples advancing by hop = sl_len/2,  "bin" = one frequency channel j with M_j
  *     coefficients per slice, "bucket" = maximal run of consecutive bins with equal M_j.
@@ -72,6 +75,8 @@ typedef struct slicq_bucket_view {
 } slicq_bucket_view;
 
 int slicq_abi_version(void);
+/* 0 = CUDA build (the product), 1 = host emulation of the kernels (test infrastructure, tests/emu) */
+int slicq_build_kind(void);
 const char* slicq_last_error(void);
 
 int slicq_plan_create(const slicq_tables* tables, slicq_plan** out);
@@ -83,7 +88,9 @@ int slicq_plan_bucket_info(const slicq_plan* plan, int b, int32_t* first_bin, in
 int64_t slicq_plan_num_slices(const slicq_plan* plan, int64_t n_samples);
 
 /* Scratch (device) bytes needed by a forward / inverse call over n_rows x n_slices units.
- * Scratch holds the per-slice spectra of one chunk; chunks are sized to stay L2 resident. */
+ * Scratch holds the intermediate spectra of one chunk of units (analysis: padded half spectra, 73.6 KB per unit;
+ * synthesis: two planes of windowed bin spectra, 147 KB per unit); SLICQ_CHUNK_MB bounds a chunk (default 2 GiB:
+ * one chunk per call -- measured faster than L2-sized chunks). */
 size_t slicq_scratch_bytes(const slicq_plan* plan, int64_t n_rows, int64_t n_slices, int inverse);
 
 /* Analysis.  x: [n_rows] rows of float32, row r at x + r*x_row_stride, n_samples valid samples

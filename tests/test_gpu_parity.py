@@ -345,3 +345,62 @@ def test_cuda_graph_capture_of_the_path(base, dev):
     assert torch.equal(y_graph, y_eager)
     assert float((y_graph[0] - 0.9 * x_new).abs().max()) < 1e-5
 
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size coefficient parity against the float64 oracle (configs[1..3] were only covered by
+# round-trip properties).  Every coefficient of every bucket, <= 1e-5 of the bucket maximum (north-star tolerance);
+# synthesis from perturbed ("model-output-like", non-range) coefficients within 5e-6 absolute for unit-scale audio.
+def _full_size_check(nsg, orc, x_np, dev, rows=None, inverse=True):
+    x = torch.from_numpy(x_np).to(dev)
+    C = nsg.forward_rows(x)                                     # [N, F, S, M]
+    sel = list(range(x_np.shape[0])) if rows is None else rows
+    O = orc.forward(x_np[sel].astype(np.float64))               # [S, n, F, M]
+    worst = 0.0
+    for c, o in zip(C, O):
+        cs = c[sel].permute(2, 0, 1, 3).cpu().numpy()
+        worst = max(worst, float(np.abs(cs - o).max() / np.abs(o).max()))
+    assert worst < REL_TOL, worst
+    if inverse:
+        P = common.perturb([o.astype(np.complex64) for o in O])  # [S, n, F, M]
+        y_ref = orc.backward([p.astype(np.complex128) for p in P], x_np.shape[-1])
+        y = nsg.backward_rows([torch.from_numpy(np.ascontiguousarray(p.transpose(1, 2, 0, 3))).to(dev) for p in P],
+                              x_np.shape[-1]).cpu().numpy()
+        assert np.abs(y - y_ref).max() < 5e-6, float(np.abs(y - y_ref).max())
+        assert snr_db(y_ref, y) > 120.0
+    return worst
+
+
+def test_full_size_parity_config1_30s_stereo(base, dev, orc):
+    """BASELINE.json configs[1]: 30 s stereo mixture [2, 1 323 000], S = 148."""
+    x = np.random.RandomState(0).rand(2, 1323000).astype(np.float32) * 2 - 1
+    _full_size_check(base.nsgt, orc, x, dev)
+
+
+def test_full_size_parity_config2_training_batch(base, dev, orc):
+    """BASELINE.json configs[2]: batch [64, 2, 88 200] = 128 rows, S = 11; rows 0, 77 and 127 against the oracle."""
+    x = np.random.RandomState(1).rand(128, 88200).astype(np.float32) * 2 - 1
+    _full_size_check(base.nsgt, orc, x, dev, rows=[0, 77, 127])
+
+
+def test_full_size_parity_config3_3min_track(base, dev, orc):
+    """BASELINE.json configs[3]: one 3-min stereo track [2, 7 938 000], S = 881, forward + inverse."""
+    x = np.random.RandomState(2).rand(2, 7938000).astype(np.float32) * 2 - 1
+    _full_size_check(base.nsgt, orc, x, dev)
+
+
+def test_masked_inverse_vs_oracle(base, dev, orc):
+    """SURVEY section 8 row A10 against the ORACLE (not against the unfused CUDA path): fused mask * mixture synthesis
+    == oracle inverse of the materialised mask * X."""
+    T = 300000
+    x = np.random.RandomState(3).rand(2, T).astype(np.float32) * 2 - 1
+    nsg = base.nsgt
+    C = nsg.forward_rows(torch.from_numpy(x).to(dev))          # [2, F, S, M]
+    rs = np.random.RandomState(4)
+    masks = [rs.rand(3, *c.shape).astype(np.float32) for c in C]            # [targets, N, F, S, M]
+    y = nsg.backward_rows_masked(C, [torch.from_numpy(m).to(dev) for m in masks], T).cpu().numpy()   # [3*2, T]
+    O = orc.forward(x.astype(np.float64))                       # [S, N, F, M]
+    Y = [np.concatenate([o * m[t].transpose(2, 0, 1, 3) for t in range(3)], axis=1) for o, m in zip(O, masks)]
+    y_ref = orc.backward(Y, T)
+    assert y.shape == y_ref.shape == (6, T)
+    assert np.abs(y - y_ref).max() < 5e-6, float(np.abs(y - y_ref).max())

@@ -48,6 +48,13 @@ def _worker(rank, world, port, T, out_dir):
         y2 = sh.inverse([torch.cat([c * 0.75, c * 0.25], dim=0) for c in C])
         assert ym.shape == y2.shape == (4, sh.hi - sh.lo)
         assert torch.equal(ym, y2), "sharded masked synthesis differs from the plain one"
+        # persistent working set (buffers and bucket views built once): repeated steps give the same bits
+        shp = SliceShardedSliCQT(nsg, T, persistent=True)
+        for _ in range(2):
+            Cp = shp.forward(sh.local_input(x))
+            assert all(torch.equal(a, b) for a, b in zip(Cp, C))
+            assert torch.equal(shp.inverse(Cp), y)
+            assert torch.equal(shp.inverse_masked(Cp, masks), ym)
         torch.save({"k0": sh.k0, "k1": sh.k1, "lo": sh.lo, "hi": sh.hi, "C": C, "y": y},
                    os.path.join(out_dir, f"rank{rank}.pt"))
         dist.barrier()

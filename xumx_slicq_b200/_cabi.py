@@ -21,7 +21,7 @@ SLICQ_E_CUDA = -3
 SLICQ_E_SCRATCH = -4
 
 EXPORTS = (
-    "slicq_abi_version", "slicq_last_error", "slicq_plan_create", "slicq_plan_destroy",
+    "slicq_abi_version", "slicq_build_kind", "slicq_last_error", "slicq_plan_create", "slicq_plan_destroy",
     "slicq_plan_n_buckets", "slicq_plan_bucket_info", "slicq_plan_num_slices",
     "slicq_scratch_bytes", "slicq_forward", "slicq_forward_packed", "slicq_forward_norm", "slicq_forward_packed_norm", "slicq_inverse", "slicq_inverse_masked", "slicq_launch_count",
     "slicq_profile_enable", "slicq_profile_read",
@@ -54,6 +54,7 @@ class SlicqError(RuntimeError):
 
 def _declare(lib: C.CDLL) -> C.CDLL:
     lib.slicq_abi_version.restype = C.c_int
+    lib.slicq_build_kind.restype = C.c_int
     lib.slicq_last_error.restype = C.c_char_p
     lib.slicq_plan_create.argtypes = [C.POINTER(SlicqTablesC), C.POINTER(C.c_void_p)]
     lib.slicq_plan_create.restype = C.c_int
@@ -131,6 +132,10 @@ def load(path: str | None = None) -> C.CDLL:
     if lib.slicq_abi_version() != 1:
         raise ImportError(f"{p}: ABI version {lib.slicq_abi_version()} != 1")
     if path is None:
+        # the product loader only takes CUDA builds: SLICQ_B200_LIB selects another build of the SAME library
+        # (tuning sweeps), never the host emulation of the test tier
+        if lib.slicq_build_kind() != 0:
+            raise ImportError(f"{p} is not a CUDA build of libslicq (host emulation libraries are test infrastructure)")
         _lib = lib
     return lib
 
@@ -188,11 +193,18 @@ class Plan:
     def scratch_bytes(self, n_rows: int, n_slices: int, inverse: bool) -> int:
         return int(self.lib.slicq_scratch_bytes(self.handle, int(n_rows), int(n_slices), int(bool(inverse))))
 
-    def _views(self, views: Sequence[tuple]):
+    def _views(self, views):
+        """ctypes array of bucket views; an array built earlier (``make_views``) passes through, so callers that
+        repeat a call on the same buffers pay for the 70 struct fills once."""
+        if isinstance(views, C.Array):
+            return views
         arr = (BucketViewC * len(views))()
         for i, (ptr, s_row, s_bin, s_slice) in enumerate(views):
             arr[i] = BucketViewC(ptr, s_row, s_bin, s_slice)
         return arr
+
+    def make_views(self, views: Sequence[tuple]):
+        return self._views(views)
 
     def forward(self, x_ptr: int, n_rows: int, x_row_stride: int, n_samples: int, t0: int, k0: int,
                 n_slices: int, views: Sequence[tuple], scratch_ptr: int, scratch_bytes: int, stream: int):

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 #ifdef SLICQ_EMU
 #include <condition_variable>
@@ -58,14 +60,15 @@ extern "C" int slicq_bins_threads(void);
 namespace {
 
 thread_local std::string g_err;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 // ---- optional per-kernel CUDA-event timing (bench.py roofline accounting) -----------------
 enum { K_SLICE_FWD = 0, K_BINS_FWD, K_BINS_INV, K_SLICE_INV, K_COUNT };
-bool g_prof = false;
+std::atomic<bool> g_prof{false};
 #ifndef SLICQ_EMU
 struct ProfRec { int kid; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof_recs;
+std::mutex g_prof_mutex;
 #endif
 struct ProfScope {
 #ifndef SLICQ_EMU
@@ -74,7 +77,7 @@ struct ProfScope {
         if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
     }
     ~ProfScope() {
-        if (on) { cudaEventRecord(b, s); ProfRec r; r.kid = kid; r.a = a; r.b = b; g_prof_recs.push_back(r); }
+        if (on) { cudaEventRecord(b, s); ProfRec r; r.kid = kid; r.a = a; r.b = b; std::lock_guard<std::mutex> lk(g_prof_mutex); g_prof_recs.push_back(r); }
     }
 #else
     ProfScope(int, cudaStream_t) {}
@@ -158,17 +161,26 @@ struct slicq_plan {
     mutable cudaStream_t side[SLICQ_MAX_WAYS];
     mutable cudaEvent_t ev_fork, ev_join[SLICQ_MAX_WAYS];
     mutable bool side_ready;
+    // calls that split share the side streams and the fork / join events: their enqueue sequence (record, waits, launches,
+    // joins) runs under this mutex, so that one thread's waits always see its own records.  Un-split calls take no lock.
+    mutable std::mutex split_mutex;
 };
 
 extern "C" int slicq_abi_version(void) { return SLICQ_ABI_VERSION; }
+#ifdef SLICQ_EMU
+extern "C" int slicq_build_kind(void) { return 1; }
+#else
+extern "C" int slicq_build_kind(void) { return 0; }
+#endif
 extern "C" const char* slicq_last_error(void) { return g_err.c_str(); }
-extern "C" int64_t slicq_launch_count(void) { return g_launches; }
+extern "C" int64_t slicq_launch_count(void) { return g_launches.load(); }
 
 extern "C" int slicq_profile_enable(int on) { g_prof = on != 0; return SLICQ_OK; }
 
 extern "C" int slicq_profile_read(double* ms, int64_t* launches) {
     for (int i = 0; i < K_COUNT; ++i) { if (ms) ms[i] = 0.0; if (launches) launches[i] = 0; }
 #ifndef SLICQ_EMU
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
     for (ProfRec& r : g_prof_recs) {
         float t = 0.f;
         if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
@@ -540,6 +552,7 @@ int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const sli
 // run `fn(row0, rows, scratch, stream)` for the row groups on the plan's side streams
 template <class F>
 int run_split(const slicq_plan* p, int64_t n_rows, int64_t n_slices, int inverse, void* scratch, cudaStream_t s, F fn) {
+    std::lock_guard<std::mutex> lock(p->split_mutex);
     if (ensure_side_streams(p)) return fail(SLICQ_E_CUDA, "cannot create internal streams");
     const int ways = split_ways(p, n_rows);
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
@@ -677,7 +690,8 @@ namespace {
 int inverse_impl(const slicq_plan* p, const slicq_bucket_view* buckets, const slicq_bucket_view* masks, int64_t x_rows,
                  int64_t n_rows, int64_t n_slices, int64_t k0, float* y, int64_t y_row_stride, int64_t length,
                  int64_t t0, float* halo_out, void* scratch, size_t scratch_bytes, void* stream) {
-    if (!p || !y || !buckets) return fail(SLICQ_E_INVALID, "null argument");
+    // y may be null when length == 0 (a shard that owns no output samples still produces its halo)
+    if (!p || (!y && length > 0) || !buckets) return fail(SLICQ_E_INVALID, "null argument");
     if (n_rows <= 0 || n_slices <= 0 || length < 0) return fail(SLICQ_E_INVALID, "bad shape");
     if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
     if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 1) || !scratch)

@@ -115,9 +115,8 @@ class NSGT_sliced(torch.nn.Module):
         self._cache = _PlanCache()
         self._adj_cache = _PlanCache()
         self._adj_tables = None
-        self._anchor = torch.zeros(1, device=self.device) if self.device.type == "cpu" else None
-        if self.device.type != "cpu":
-            self._anchor = torch.zeros(1, device=self.device)
+        self._anchor = torch.zeros(1, device=self.device)
+        self.device = self._anchor.device        # "cuda" -> "cuda:<current>": comparable with tensor.device
 
     # -- reference-visible window tables (host copies, for inspection / visualisation) -----
     def _split(self, flat: np.ndarray) -> List[torch.Tensor]:
@@ -232,6 +231,24 @@ class NSGT_sliced(torch.nn.Module):
                                 scratch.data_ptr(), nbytes, _BACKEND.stream(x.device))
         return out
 
+    def forward_rows_into(self, ctx: dict, x: torch.Tensor, k0: int = 0, n_slices: int | None = None, t0: int = 0):
+        """``forward_rows`` into buffers kept in ``ctx`` (coefficient slab, bucket tensors, scratch): repeated calls of
+        one shape allocate nothing and rebuild no views.  The returned tensors are overwritten by the next call."""
+        _BACKEND.check(x)
+        N, T = x.shape
+        S = self.n_slices(T) if n_slices is None else int(n_slices)
+        plan = self.plan(x.device)
+        key = (N, S, x.device)
+        with _BACKEND.device_guard(x.device):
+            if ctx.get("fwd_key") != key:
+                ctx["slab"], ctx["coefs"] = self.alloc_coefficients(N, S, x.device)
+                ctx["fwd_bytes"] = plan.scratch_bytes(N, S, False)
+                ctx["fwd_scratch"] = torch.empty(ctx["fwd_bytes"], dtype=torch.uint8, device=x.device)
+                ctx["fwd_key"] = key
+            plan.forward_packed(x.data_ptr(), N, x.stride(0), T, int(t0), int(k0), S, ctx["slab"].data_ptr(),
+                                ctx["fwd_scratch"].data_ptr(), ctx["fwd_bytes"], _BACKEND.stream(x.device))
+        return ctx["coefs"]
+
     def forward(self, sig: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         """slicq.py:182-196: ``sig`` is a 1-tuple holding [N, T]; returns list of [S, N, F_b, M_b]."""
         (x,) = sig
@@ -239,9 +256,19 @@ class NSGT_sliced(torch.nn.Module):
 
     # -- synthesis --------------------------------------------------------------------------
     def backward_rows(self, coefs: Sequence[torch.Tensor], length: int, k0: int = 0, t0: int = 0,
-                      halo_out: torch.Tensor | None = None) -> torch.Tensor:
-        """list of complex [N, F_b, S, M_b] (any strides, M contiguous) -> [N, length] float32."""
+                      halo_out: torch.Tensor | None = None, ctx: dict | None = None) -> torch.Tensor:
+        """list of complex [N, F_b, S, M_b] (any strides, M contiguous) -> [N, length] float32.
+        ``ctx`` (a dict the caller keeps, keyed by the input tensors): bucket views, scratch and the output tensor
+        are built once and reused by later calls on the same tensors."""
         t = self.tables
+        if ctx is not None and "inv_views" in ctx:
+            plan = self.plan(coefs[0].device)
+            y = ctx["y"]
+            with _BACKEND.device_guard(coefs[0].device):
+                plan.inverse(ctx["inv_views"], ctx["inv_N"], ctx["inv_S"], int(k0), y.data_ptr(), y.stride(0) if y.shape[1] else 1,
+                             y.shape[1], int(t0), halo_out.data_ptr() if halo_out is not None else 0,
+                             ctx["inv_scratch"].data_ptr(), ctx["inv_bytes"], _BACKEND.stream(coefs[0].device))
+            return y
         if len(coefs) != len(t.buckets):
             raise ValueError(f"expected {len(t.buckets)} coefficient buckets, got {len(coefs)}")
         c0 = coefs[0]
@@ -269,17 +296,29 @@ class NSGT_sliced(torch.nn.Module):
             plan.inverse(views, N, S, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len, int(t0),
                          halo_out.data_ptr() if halo_out is not None else 0,
                          scratch.data_ptr(), nbytes, _BACKEND.stream(c0.device))
+        if ctx is not None:
+            ctx.update(inv_views=plan.make_views(views), inv_N=N, inv_S=S, y=y, inv_scratch=scratch, inv_bytes=nbytes, keep=keep)
         del keep
         return y
 
     def backward_rows_masked(self, mix: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], length: int,
-                             k0: int = 0, t0: int = 0, halo_out: torch.Tensor | None = None) -> torch.Tensor:
+                             k0: int = 0, t0: int = 0, halo_out: torch.Tensor | None = None,
+                             ctx: dict | None = None) -> torch.Tensor:
         """Synthesis fused with mask * mixture (realtime model, phase.py:96-113 / model.py:258-265).
 
         mix: per bucket complex [N, F_b, S, M_b]; masks: per bucket float32 [T, N, F_b, S, M_b].
         Returns [T * N, length] (row t * N + n) = inverse of masks[t, n] * mix[n], bitwise equal to
         ``backward_rows([ (m * x).flatten(0, 1) ])`` without materialising the T coefficient sets."""
         t = self.tables
+        if ctx is not None and "m_views" in ctx:
+            plan = self.plan(mix[0].device)
+            y = ctx["y"]
+            with _BACKEND.device_guard(mix[0].device):
+                plan.inverse_masked(ctx["x_views"], ctx["m_views"], ctx["inv_T"], ctx["inv_N"], ctx["inv_S"], int(k0), y.data_ptr(),
+                                    y.stride(0) if y.shape[1] else 1, y.shape[1], int(t0),
+                                    halo_out.data_ptr() if halo_out is not None else 0,
+                                    ctx["inv_scratch"].data_ptr(), ctx["inv_bytes"], _BACKEND.stream(mix[0].device))
+            return y
         if len(mix) != len(t.buckets) or len(masks) != len(t.buckets):
             raise ValueError(f"expected {len(t.buckets)} buckets")
         c0 = mix[0]
@@ -310,6 +349,9 @@ class NSGT_sliced(torch.nn.Module):
             plan.inverse_masked(vx, vm, Tn, N, S, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len,
                                 int(t0), halo_out.data_ptr() if halo_out is not None else 0,
                                 scratch.data_ptr(), nbytes, _BACKEND.stream(c0.device))
+        if ctx is not None:
+            ctx.update(x_views=plan.make_views(vx), m_views=plan.make_views(vm), inv_T=Tn, inv_N=N, inv_S=S, y=y,
+                       inv_scratch=scratch, inv_bytes=nbytes, keep=keep)
         del keep
         return y
 
@@ -318,15 +360,22 @@ class NSGT_sliced(torch.nn.Module):
         _BACKEND.check(t)
 
     def backward_views(self, views, n_rows: int, n_slices: int, device, length: int, k0: int = 0, t0: int = 0,
-                       halo_out: torch.Tensor | None = None) -> torch.Tensor:
+                       halo_out: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """Synthesis from precomputed (ptr, s_row, s_bin, s_slice) bucket views (complex64 element
-        strides); the caller keeps the tensors alive and guarantees shapes / 16-byte alignment."""
+        strides); the caller keeps the tensors alive and guarantees shapes / 16-byte alignment.
+        ``out``: optional float32 [n_rows, out_len] tensor (unit stride along samples) to write into."""
         t = self.tables
         length = int(length)
         out_len = max(0, min(length, (int(k0) + n_slices) * t.hop - int(t0)))
         plan = self.plan(device)
         with _BACKEND.device_guard(device):
-            y = torch.empty((n_rows, out_len), dtype=torch.float32, device=device)
+            if out is not None:
+                if tuple(out.shape) != (n_rows, out_len) or out.dtype != torch.float32 or out.device != device or \
+                        (out_len > 1 and out.stride(1) != 1):
+                    raise ValueError(f"out must be a float32 [{n_rows}, {out_len}] tensor on {device}")
+                y = out
+            else:
+                y = torch.empty((n_rows, out_len), dtype=torch.float32, device=device)
             nbytes = plan.scratch_bytes(n_rows, n_slices, True)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             plan.inverse(views, n_rows, n_slices, int(k0), y.data_ptr(), y.stride(0) if out_len else 1, out_len,

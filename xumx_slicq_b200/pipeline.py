@@ -32,7 +32,8 @@ class TransformStream:
         self.s_out = torch.cuda.Stream(self.device)
         self._xd: List[Optional[torch.Tensor]] = [None] * self.depth
         self._yd: List[Optional[torch.Tensor]] = [None] * self.depth
-        self._yh: List[Optional[torch.Tensor]] = [None] * self.depth
+        # one more host slot than batches in flight: a result stays valid while the next `depth - 1` are produced
+        self._yh: List[Optional[torch.Tensor]] = [None] * (self.depth + 1)
 
     def _buf(self, store, i, shape, device, pinned=False):
         t = store[i]
@@ -44,23 +45,22 @@ class TransformStream:
         return t
 
     def process(self, batches: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
-        """batches: pinned host tensors [B, C, T] float32.  Yields pinned host tensors with the
-        inverse transform of the model output (valid until `depth` further batches were yielded)."""
+        """batches: pinned host tensors [B, C, T] float32.  Yields pinned host tensors [targets, B, C, T] with the inverse
+        transform of the model output.  A yielded tensor stays valid until the generator has been advanced `depth` more
+        times (it is one of depth + 1 rotating pinned buffers): copy it if it has to live longer."""
+        nh = self.depth + 1
         ev_in = [torch.cuda.Event() for _ in range(self.depth)]
         ev_cmp = [torch.cuda.Event() for _ in range(self.depth)]
-        ev_out = [torch.cuda.Event() for _ in range(self.depth)]
-        used = [False] * self.depth
-        pending = []          # slots whose output copy has been queued, in order
+        ev_out = [torch.cuda.Event() for _ in range(nh)]
+        pending = []          # (device slot, host slot) whose output copy has been queued, oldest first
         for i, xh in enumerate(batches):
-            b = i % self.depth
+            b, hb = i % self.depth, i % nh
             T = xh.shape[-1]
-            if used[b]:
-                # slot reuse: its previous D2H must have finished before we overwrite buffers;
-                # hand that result out first
-                while pending and pending[0] == b:
-                    ev_out[b].synchronize()
-                    pending.pop(0)
-                    yield self._yh[b]
+            # device slot b was used by batch i - depth: its D2H has to be over before the buffers are overwritten
+            while pending and (pending[0][0] == b or len(pending) >= self.depth):
+                pb, ph = pending.pop(0)
+                ev_out[ph].synchronize()
+                yield self._yh[ph]
             xd = self._buf(self._xd, b, xh.shape, self.device)
             with torch.cuda.stream(self.s_in):
                 xd.copy_(xh, non_blocking=True)
@@ -69,23 +69,20 @@ class TransformStream:
                 self.s_cmp.wait_event(ev_in[b])
                 X = self.nsgt(xd)
                 Y = self.model(X)
-                y = self.insgt(Y, T)
-                yd = self._buf(self._yd, b, y.shape, self.device)
-                yd.copy_(y)
+                lead = tuple(Y[0].shape[:-4])
+                yd = self._buf(self._yd, b, lead + (T,), self.device)
+                try:
+                    self.insgt(Y, T, out=yd)        # straight into the staging buffer: no extra device copy
+                except ValueError:
+                    yd.copy_(self.insgt(Y, T))      # model outputs that are not contiguous float32
                 ev_cmp[b].record(self.s_cmp)
-                del X, Y, y
-            yh = self._buf(self._yh, b, yd.shape, "cpu", pinned=True)
+                del X, Y
+            yh = self._buf(self._yh, hb, yd.shape, "cpu", pinned=True)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp[b])
                 yh.copy_(yd, non_blocking=True)
-                ev_out[b].record(self.s_out)
-            used[b] = True
-            pending.append(b)
-            # hand out everything that is already complete, keeping up to depth-1 batches in flight
-            while len(pending) >= self.depth:
-                pb = pending.pop(0)
-                ev_out[pb].synchronize()
-                yield self._yh[pb]
-        for pb in pending:
-            ev_out[pb].synchronize()
-            yield self._yh[pb]
+                ev_out[hb].record(self.s_out)
+            pending.append((b, hb))
+        for pb, ph in pending:
+            ev_out[ph].synchronize()
+            yield self._yh[ph]

@@ -140,12 +140,14 @@ class INSGT_SL(nn.Module):
         self.nsgt._apply(fn)
         return self
 
-    def forward(self, X_list, length: int) -> Tensor:
+    def forward(self, X_list, length: int, out: Tensor = None) -> Tensor:
+        """transforms.py:154-178.  ``out`` (extension, optional): a contiguous float32 tensor of the result's shape
+        to write into (staging buffers of a copy pipeline: saves one device copy); contiguous float32 inputs only."""
         if torch.is_grad_enabled() and any(X.requires_grad for X in X_list):
             return _InverseFn.apply(self, length, *X_list)
-        return self._forward_impl(X_list, length)
+        return self._forward_impl(X_list, length, out)
 
-    def _forward_impl(self, X_list, length: int) -> Tensor:
+    def _forward_impl(self, X_list, length: int, out: Tensor = None) -> Tensor:
         dev = _module_device(self.nsgt)
         nsg = self.nsgt.nsgt
         buckets = nsg.tables.buckets
@@ -165,8 +167,15 @@ class INSGT_SL(nn.Module):
                     raise ValueError(f"bucket shape {tuple(X.shape)} != {lead + (nb, S, M, 2)}")
                 views.append((X.data_ptr(), nb * S * M, S * M, M))
             nsg._BACKEND_check(X0)
-            y = nsg.backward_views(views, rows, S, dev, length)
+            o2 = None
+            if out is not None:
+                if not out.is_contiguous() or tuple(out.shape[:-1]) != lead:
+                    raise ValueError("out must be contiguous with the leading dimensions of the coefficients")
+                o2 = out.view(rows, -1)
+            y = nsg.backward_views(views, rows, S, dev, length, out=o2)
             return y.view(*lead, -1)
+        if out is not None:
+            raise ValueError("out= needs contiguous float32 coefficient tensors on the transform's device")
         cs = []
         lead = None
         for X in X_list:
