@@ -182,62 +182,86 @@ def cpu_reference_arm(steps: int, warmup: int, sample_seconds: float):
     return sample_seconds / dt, dt, cores, sample, kind, len(times)
 
 
-def bench_slices(args, nsg, dev, rank, world, distributed):
-    """BASELINE.json configs[3]: ONE synthetic 3-min stereo track; slices split into contiguous ranges
-    over the ranks, one half-slice halo message per boundary over NCCL (strong scaling)."""
+def slice_sharding_run(nsg, dev, rank, world, steps: int, warmup: int):
+    """BASELINE.json configs[3]: ONE synthetic 3-min stereo track (881 slices), 1 forward + 4-target synthesis fused with
+    mask * mixture; slices split into contiguous ranges over the ranks, one [rows, 9030] fp32 halo message per boundary
+    and direction over NCCL.  Every rank also runs the unsharded track on its own GPU (the 1-GPU time of the same work)
+    and checks its shard against it bit for bit.  Returns a dict on every rank (max over ranks where it matters)."""
     import torch
     import torch.distributed as dist
     from xumx_slicq_b200.sharding import SliceShardedSliCQT
     Ttrack = 180 * FS
-    if distributed:
-        sh = SliceShardedSliCQT(nsg, Ttrack)
-        lo, hi = sh.lo, sh.hi
-    else:
-        sh, lo, hi = None, 0, Ttrack
+    distributed = world > 1
     gen = torch.Generator(device=dev).manual_seed(7)
-    x_local = (torch.rand(2, Ttrack, device=dev, generator=gen) * 2 - 1)[:, lo:hi].contiguous()
-    gains = GAINS
-
-    # model stand-in: constant masks (the gain of each target), prepared once -- the timed step is the transform:
-    # forward of the shard, synthesis of the 4 targets fused with mask * mixture, halo exchange
-    C0 = sh.forward(x_local) if sh else nsg.forward_rows(x_local)
-    masks = [torch.stack([torch.full(tuple(c.shape), g, dtype=torch.float32, device=dev) for g in gains]) for c in C0]
-    del C0
-
-    def step():
-        C = sh.forward(x_local) if sh else nsg.forward_rows(x_local)
-        return sh.inverse_masked(C, masks) if sh else nsg.backward_rows_masked(C, masks, Ttrack)
-
-    for _ in range(args.warmup):
-        y = step()
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+    x = torch.rand(2, Ttrack, device=dev, generator=gen) * 2 - 1
     stream = torch.cuda.current_stream(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(args.steps):
-        y = step()
-    b.record(stream)
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    err = float((y[:2] - gains[0] * x_local).abs().max())
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            y = step()
+        b.record(stream)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), y
+
+    # unsharded (what one GPU does alone), same buffers reused every step
+    ctx1, ctx1i = {}, {}
+    C1 = nsg.forward_rows_into(ctx1, x)
+    masks1 = [torch.stack([torch.full(tuple(c.shape), g, dtype=torch.float32, device=dev) for g in GAINS]) for c in C1]
+
+    def step1():
+        C = nsg.forward_rows_into(ctx1, x)
+        return nsg.backward_rows_masked(C, masks1, Ttrack, ctx=ctx1i)
+    ms1, y1 = timed(step1)
+    out = {"ms_per_step_1gpu": ms1, "n_gpus": world}
+    if not distributed:
+        out.update(ms_per_step=ms1, speedup_vs_1=1.0, bitwise_equal=True,
+                   max_abs_err_target0=float((y1[:2] - GAINS[0] * x).abs().max()))
+        return out
+    sh = SliceShardedSliCQT(nsg, Ttrack, persistent=True)
+    x_local = sh.local_input(x)
+    masks = [m[:, :, :, sh.k0:sh.k1].contiguous() for m in masks1]
+
+    def stepn():
+        C = sh.forward(x_local)
+        return sh.inverse_masked(C, masks)
+    msn, yn = timed(stepn)
+    Cn = sh.forward(x_local)
+    ok = all(torch.equal(pc, fc[:, :, sh.k0:sh.k1]) for pc, fc in zip(Cn, C1)) and torch.equal(yn, y1[:, sh.lo:sh.hi])
+    flag = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out.update(ms_per_step=msn, speedup_vs_1=ms1 / msn, bitwise_equal=bool(int(flag.item())),
+               slices_per_rank=sh.k1 - sh.k0, halo_bytes_per_boundary_and_direction=[2 * sh.hop * 4, 8 * sh.hop * 4],
+               max_abs_err_target0=float((yn[:2] - GAINS[0] * x_local).abs().max()))
+    return out
+
+
+def bench_slices(args, nsg, dev, rank, world, distributed):
+    """`--mode slices`: the configs[3] line on its own (strong scaling)."""
+    import torch.distributed as dist
+    r = slice_sharding_run(nsg, dev, rank, world, args.steps, args.warmup)
     if rank == 0:
         emit(({
-            "metric": "sliCQT fwd+inv audio-sec/sec", "value": 180.0 / (ms * 1e-3), "unit": "audio-s/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "metric": "sliCQT fwd+inv audio-sec/sec", "value": 180.0 / (r["ms_per_step"] * 1e-3), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[3]: one synthetic 3-min stereo track (881 slices), 1 forward + 4-target "
                                    "inverse, slices sharded in contiguous ranges, one [rows, 9030] fp32 halo message "
                                    "per boundary and direction over NCCL; the 4 targets are mask * mixture fused into the synthesis "
                                    "(constant masks as the model stand-in)",
                        "parallelism": f"slices x{world}"},
-            "max_abs_err_target0": err,
+            "slice_sharding": r, "max_abs_err_target0": r["max_abs_err_target0"],
         }))
     if distributed:
         dist.destroy_process_group()
@@ -657,6 +681,13 @@ def main():
                  "max_abs_err_target0": ferr}
         del masks, nslab
 
+    # ---- configs[3] beside the headline when there is more than one GPU: one 3-min track sharded by slice range over NCCL
+    shard = None
+    if distributed:
+        del Y, Cout, slab, scratch, yout
+        torch.cuda.empty_cache()
+        shard = slice_sharding_run(nsg, dev, rank, world, 20, 3)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores, sample, kind, _ = cpu_reference_arm(5, 1, args.cpu_sample_seconds)
@@ -669,6 +700,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_mixture": single, "fused_step": fused,
+            "slice_sharding": shard,
             "gpu_launches": int(launches),
             "clocks": clocks, "max_abs_err_target0": err,
         }))

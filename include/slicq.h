@@ -63,6 +63,12 @@ typedef struct slicq_tables {
  * bins reaching outside [0, L/2] read zeros instead of the Hermitian mirror; the caller passes
  * tukey = 1 and win_fwd = gd * M^2. */
 #define SLICQ_PLAN_ADJOINT_OF_SYNTHESIS 1
+/* Plan flag: the SYNTHESIS entry of this plan computes the adjoint (transpose) of the ANALYSIS of the normal plan --
+ * autograd through NSGT_SL (the reference gets it from torch autograd on nsgt/slicing.py + nsgt/nsgtf.py,
+ * training.py:77-95).  Bin spectra that reach below DC / above Nyquist are folded back (conjugated) instead of
+ * dropped, DC / Nyquist count twice, and the slice is multiplied by the slicing window before the overlap-add; the
+ * caller passes win_inv = g * L / (2 M^2) and the normal tukey. */
+#define SLICQ_PLAN_ADJOINT_OF_ANALYSIS 2
 
 typedef struct slicq_plan slicq_plan; /* opaque */
 

@@ -215,5 +215,30 @@ def test_inverse_autograd_is_the_exact_adjoint(base):
     fd = float(((y2 - y.detach()).double() * g.double()).sum()) / 0.5
     an = float(sum((db.double() * Xb.grad.double()).sum() for db, Xb in zip(d, X)))
     assert abs(fd - an) <= 2e-4 * max(abs(an), 1.0), (fd, an)
-    with pytest.raises(NotImplementedError):
-        nsgt(x.clone().requires_grad_(True))
+
+
+def test_forward_autograd_is_the_exact_adjoint(base):
+    """SURVEY section 8(f) N3, other direction: gradients through NSGT_SL (adjoint of the analysis on the synthesis
+    kernels).  <A x, d> == <x, A^T d>, a directional derivative, and the chain forward -> inverse."""
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(base)
+    T = 14000
+    x = torch.from_numpy(common.small_input()[:, :T]).view(1, 2, -1).contiguous().requires_grad_(True)
+    X = nsgt(x)
+    assert all(Xb.requires_grad for Xb in X)
+    d = [torch.randn(Xb.shape, generator=torch.Generator().manual_seed(11 + i)) for i, Xb in enumerate(X)]
+    sum((Xb * db).sum() for Xb, db in zip(X, d)).backward()
+    lhs = float(sum((Xb.detach().double() * db.double()).sum() for Xb, db in zip(X, d)))
+    rhs = float((x.detach().double() * x.grad.double()).sum())
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), 1.0), (lhs, rhs)          # <A x, d> == <x, A^T d>
+    e = torch.randn(x.shape, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        X2 = nsgt(x.detach() + 0.25 * e)
+    fd = float(sum(((b2 - b1.detach()).double() * db.double()).sum() for b1, b2, db in zip(X, X2, d))) / 0.25
+    an = float((e.double() * x.grad.double()).sum())
+    assert abs(fd - an) <= 2e-4 * max(abs(an), 1.0), (fd, an)
+    # reconstruction loss through both transforms: d/dx 0.5 |insgt(nsgt(x)) - t|^2 = (perfect reconstruction) x - t
+    x2 = x.detach().clone().requires_grad_(True)
+    tgt = torch.randn(x.shape, generator=torch.Generator().manual_seed(6))
+    (0.5 * (insgt(nsgt(x2), T) - tgt) ** 2).sum().backward()
+    assert float((x2.grad - (x2.detach() - tgt)).abs().max()) < 2e-4

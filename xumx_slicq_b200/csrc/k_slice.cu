@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     float2* __restrict__ H = p.spec + (long long)rsl * p.spec_stride + p.t.pad_l;
     const int pad_l = p.t.pad_l, pad_r = p.t.pad_r;
     const float sc = 0.5f * p.t.spec_scale, se = p.t.ends_scale;
-    const float mir = p.t.adjoint ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
+    const float mir = (p.t.adjoint & 1) ? 0.f : 1.f;     // adjoint mode: positions outside [0, N] read as zero
     constexpr int NP2 = (N / 2 + NT) / NT;      // pairs (k, N-k) per thread
     float2 wkv[NP2];
 #pragma unroll
@@ -288,6 +288,22 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             if (q.z >= 0) { const float2 v = __ldg(Trow + q.z); e.x += v.x; e.y += v.y; }
             Z[q.x].x += e.x; Z[q.x].y += e.y;
         }
+        if (p.t.adjoint & 2) {
+            // adjoint of the analysis: what the bins put below DC / above Nyquist folds back conjugated (the analysis
+            // READS the Hermitian mirror there); positions 1 .. pad_l and N - pad_r .. N - 1, disjoint from the entries above
+            // only in time: order them after the overflow pass
+            __syncthreads();
+            const float2* __restrict__ P0 = Trow + p.t.pl_off;
+            const float2* __restrict__ P1 = P0 + p.t.pl_len;
+            for (int f = 1 + tid; f <= p.t.pad_l; f += NT) {
+                const float2 a = __ldg(P0 - f), b = __ldg(P1 - f);
+                Z[f].x += a.x + b.x; Z[f].y -= a.y + b.y;
+            }
+            for (int f = 1 + tid; f <= p.t.pad_r; f += NT) {
+                const float2 a = __ldg(P0 + N + f), b = __ldg(P1 + N + f);
+                Z[N - f].x += a.x + b.x; Z[N - f].y -= a.y + b.y;
+            }
+        }
     }
     // ---- Hermitian pre-processing, in place: Z[k] = E + i conj(w^k) O, Z[N-k] = conj(E - i conj(w^k) O)
     {
@@ -307,7 +323,8 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             const cpx rn = cpx_ld(Z + N - kk);
             if (kk == 0) {
                 // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
-                const float a = cpx_re(rk), b = cpx_re(rn);
+                const float es = (p.t.adjoint & 2) ? 2.f : 1.f;     // adjoint of the analysis: DC / Nyquist count twice
+                const float a = cpx_re(rk) * es, b = cpx_re(rn) * es;
                 Z[0] = make_float2(a + b, a - b);
             } else {
                 const cpx E = caddc(rk, rn);                 // rk + conj(rn)
@@ -364,6 +381,12 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const bool vec = ((reinterpret_cast<uintptr_t>(yr + tb) & 7) == 0) && tb >= 0 && tb + 2 * N <= p.T && !first_to_halo;
     const bool add1 = accumulate, add2 = accumulate && !second_store;
     if (SLICQ_DBG_SKIP & 8) return;
+    if (p.t.adjoint & 2) {
+        // adjoint of the analysis: the slicing window multiplies the slice before the overlap-add
+        const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
+        for (int n = tid; n < N; n += NT) { const float2 w = __ldg(tw2 + n); Z[n].x *= w.x; Z[n].y *= w.y; }
+        // every thread reads back exactly the elements it scaled (same n = tid + i NT below): no barrier
+    }
     if (vec && add1 == add2) {
         float2* __restrict__ y2 = reinterpret_cast<float2*>(yr + tb);
         constexpr int U = 7;

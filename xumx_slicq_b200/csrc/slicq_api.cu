@@ -356,26 +356,27 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     }
     const int n_ex = (int)ex.size();
     if (ex.empty()) ex.push_back(int4{0, 0, -1, 0});
-    // gaps: positions 0 .. N2 + 1 of a plane that none of its bins covers; owner = the next bin of the plane (or its last)
+    // gaps: positions of a plane row (-pl_off .. pl_len - pl_off - 1, margins included: the adjoint-of-analysis mode folds
+    // them back) that none of its bins covers; owner = the next bin of the plane (or its last)
     std::vector<int2> gaps;
     {
         std::vector<std::vector<int2> > per_bucket(p->buckets.size());
         auto bucket_of = [&](int j) { for (size_t i = 0; i < p->buckets.size(); ++i) if (j >= p->buckets[i].first_bin && j < p->buckets[i].first_bin + p->buckets[i].n_bins) return (int)i; return 0; };
         for (int q = 0; q < 2; ++q) {
-            std::vector<int> owner(N2 + 2, -1);    // covering bin or -1
+            std::vector<int> owner(pl_len, -1);    // covering bin or -1, index = pl_off + f
             int last = -1;
             for (int j = q; j < J; j += 2) {
-                const int lo = std::max(0, p->bin_pos[j] - p->bin_M[j] / 2), hi = std::min(N2 + 2, p->bin_pos[j] + p->bin_M[j] / 2);
+                const int lo = std::max(0, pl_off + p->bin_pos[j] - p->bin_M[j] / 2), hi = std::min(pl_len, pl_off + p->bin_pos[j] + p->bin_M[j] / 2);
                 for (int f = lo; f < hi; ++f) owner[f] = j;
                 last = j;
             }
             if (last < 0) { delete p; return fail(SLICQ_E_UNSUPPORTED, "a bin plane is empty"); }
-            for (int f = 0; f < N2 + 2;) {
+            for (int f = 0; f < pl_len;) {
                 if (owner[f] >= 0) { ++f; continue; }
                 int g = f;
-                while (g < N2 + 2 && owner[g] < 0) ++g;
-                const int next = g < N2 + 2 ? owner[g] : last;
-                per_bucket[bucket_of(next)].push_back(int2{q * pl_len + pl_off + f, g - f});
+                while (g < pl_len && owner[g] < 0) ++g;
+                const int next = g < pl_len ? owner[g] : last;
+                per_bucket[bucket_of(next)].push_back(int2{q * pl_len + f, g - f});
                 f = g;
             }
         }
@@ -390,9 +391,9 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
     d.pad_l = pad_l; d.pad_r = pad_r; d.tw_lo = tw_lo; d.tw_hi = tw_hi;
-    d.adjoint = (t->flags & SLICQ_PLAN_ADJOINT_OF_SYNTHESIS) ? 1 : 0;
-    d.spec_scale = d.adjoint ? (float)(2.0 / L) : 1.f;
-    d.ends_scale = d.adjoint ? (float)(1.0 / L) : 1.f;
+    d.adjoint = t->flags & (SLICQ_PLAN_ADJOINT_OF_SYNTHESIS | SLICQ_PLAN_ADJOINT_OF_ANALYSIS);
+    d.spec_scale = (d.adjoint & 1) ? (float)(2.0 / L) : 1.f;
+    d.ends_scale = (d.adjoint & 1) ? (float)(1.0 / L) : 1.f;
     int rc = 0;
     rc |= upload(tuk, &d.tukey, p->owned);
     rc |= upload(wf, &d.wf, p->owned);

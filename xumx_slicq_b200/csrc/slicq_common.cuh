@@ -136,7 +136,8 @@ struct SlicqDeviceTables {
     int pad_l;      // spectrum rows carry pad_l mirrored bins below DC ...
     int pad_r;      // ... and pad_r mirrored bins above Nyquist (bins never need reflection logic)
     int tw_lo, tw_hi;       // support of the slicing window: tukey[p] != 0 only for p in [tw_lo, tw_hi)
-    int adjoint;            // 1: analysis kernels compute the adjoint of the synthesis (see include/slicq.h)
+    int adjoint;            // bit 0: analysis kernels compute the adjoint of the synthesis; bit 1: synthesis kernels that of
+                            // the analysis (include/slicq.h SLICQ_PLAN_ADJOINT_OF_*)
     float spec_scale;       // factor on the slice spectrum (1, or 2/L in adjoint mode) ...
     float ends_scale;       // ... and on its DC / Nyquist bins (1, or 1/L)
     const float* tukey;     // [L]   slicing window

@@ -63,6 +63,20 @@ class _AdjointTables:
         self.flags = 1
 
 
+class _AdjointAnalysisTables:
+    """Tables of the plan whose SYNTHESIS entry is the adjoint of the normal plan's ANALYSIS
+    (include/slicq.h: SLICQ_PLAN_ADJOINT_OF_ANALYSIS): analysis windows g * L / (2 M^2) in place of the duals."""
+
+    def __init__(self, t):
+        self.sllen, self.n_bins = t.sllen, t.n_bins
+        self.bin_M, self.bin_pos = t.bin_M, t.bin_pos
+        s = np.concatenate([np.full(int(m), float(t.sllen) / (2.0 * float(m) * float(m)), dtype=np.float64) for m in t.bin_M])
+        self.win_fwd = t.win_fwd
+        self.win_inv = (t.win_fwd.astype(np.float64) * s).astype(np.float32)
+        self.tukey = t.tukey
+        self.flags = 2
+
+
 class _PlanCache:
     """Per-device `slicq_plan` handles, created lazily; never copied (ctypes handles)."""
 
@@ -115,6 +129,8 @@ class NSGT_sliced(torch.nn.Module):
         self._cache = _PlanCache()
         self._adj_cache = _PlanCache()
         self._adj_tables = None
+        self._adja_cache = _PlanCache()
+        self._adja_tables = None
         self._anchor = torch.zeros(1, device=self.device)
         self.device = self._anchor.device        # "cuda" -> "cuda:<current>": comparable with tensor.device
 
@@ -405,6 +421,24 @@ class NSGT_sliced(torch.nn.Module):
             plan.forward_packed(g.data_ptr(), N, g.stride(0), T, 0, 0, n_slices, slab.data_ptr(),
                                 scratch.data_ptr(), nbytes, _BACKEND.stream(g.device))
         return out
+
+    def analysis_adjoint_views(self, views, n_rows: int, n_slices: int, device, length: int) -> torch.Tensor:
+        """Gradient of the analysis: per-bucket views of d [N, F_b, S, M_b] complex (gradient w.r.t. the coefficients) ->
+        [N, length] float32 = A^T d, the transpose of ``forward_rows`` with respect to the real inner products
+        <c, d> = sum Re(c) Re(d) + Im(c) Im(d), <x, g> = sum x g.  Runs on the SYNTHESIS kernels with a third plan
+        (analysis windows instead of duals, out-of-band bin parts folded back, slicing window before the overlap-add)."""
+        if self._adja_tables is None:
+            self._adja_tables = _AdjointAnalysisTables(self.tables)
+        plan = self._adja_cache.get(self._adja_tables, device)
+        length = int(length)
+        with _BACKEND.device_guard(device):
+            # the analysis zero-extends the signal: slices reach past `length`, their gradient there is dropped
+            y = torch.empty((n_rows, length), dtype=torch.float32, device=device)
+            nbytes = plan.scratch_bytes(n_rows, n_slices, True)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            plan.inverse(views, n_rows, n_slices, 0, y.data_ptr(), y.stride(0) if length else 1, length, 0, 0,
+                         scratch.data_ptr(), nbytes, _BACKEND.stream(device))
+        return y
 
     def backward(self, cseq: Sequence[torch.Tensor], length: int) -> torch.Tensor:
         """slicq.py:198-230: list of [S, N, F_b, M_b] complex -> [N, length].

@@ -86,9 +86,7 @@ class NSGT_SL(nn.Module):
         if x.device != dev and x.device.type == "cpu":
             x = x.to(dev)
         if torch.is_grad_enabled() and x.requires_grad:
-            raise NotImplementedError(
-                "gradients w.r.t. the analysed waveform are not implemented (the reference never needs them: "
-                "training.py feeds data tensors); gradients through INSGT_SL are (see _InverseFn)")
+            return list(_ForwardFn.apply(self, x))
         x = x.contiguous().view(-1, shape[-1])
         return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True)
 
@@ -103,6 +101,40 @@ class NSGT_SL(nn.Module):
             x = x.to(dev)
         x = x.contiguous().view(-1, shape[-1])
         return self.nsgt.nsgt.forward_rows(x, lead=tuple(shape[:-1]), as_real=True, with_norm=True)
+
+
+class _ForwardFn(torch.autograd.Function):
+    """Differentiable analysis: forward = NSGT kernels, backward = their exact adjoint on the synthesis kernels
+    (third plan, SLICQ_PLAN_ADJOINT_OF_ANALYSIS).  The reference gets this gradient from torch autograd over
+    nsgt/slicing.py + nsgt/nsgtf.py (training.py:77-95 when the input requires grad)."""
+
+    @staticmethod
+    def forward(ctx, module, x):
+        ctx.module = module
+        ctx.xshape = tuple(x.shape)
+        with torch.no_grad():
+            X = module.forward(x.detach())
+        ctx.S = X[0].shape[-3]
+        return tuple(X)
+
+    @staticmethod
+    def backward(ctx, *gX):
+        module = ctx.module
+        nsg = module.nsgt.nsgt
+        dev = _module_device(module.nsgt)
+        rows = 1
+        for d in ctx.xshape[:-1]:
+            rows *= d
+        views, keep = [], []
+        for g, (_, nb, M) in zip(gX, nsg.tables.buckets):
+            if g is None:
+                g = torch.zeros(ctx.xshape[:-1] + (nb, ctx.S, M, 2), dtype=torch.float32, device=dev)
+            g = g.to(torch.float32).contiguous()
+            keep.append(g)
+            views.append((g.data_ptr(), nb * ctx.S * M, ctx.S * M, M))
+        gx = nsg.analysis_adjoint_views(views, rows, ctx.S, dev, ctx.xshape[-1])
+        del keep
+        return None, gx.view(ctx.xshape)
 
 
 class _InverseFn(torch.autograd.Function):
