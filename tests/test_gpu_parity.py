@@ -423,3 +423,20 @@ def test_masked_inverse_vs_oracle(base, dev, orc):
     y_ref = orc.backward(Y, T)
     assert y.shape == y_ref.shape == (6, T)
     assert np.abs(y - y_ref).max() < 5e-6, float(np.abs(y - y_ref).max())
+
+
+def test_streamed_separator_overlap_exact(base, dev):
+    """SURVEY section 8(f) N2 on the GPU: a 2-min signal in ~59 s chunks (the reference's chunk size) and in small chunks,
+    bitwise equal to the unchunked path for a slice-local model."""
+    from xumx_slicq_b200 import make_filterbanks
+    from xumx_slicq_b200.pipeline import StreamedSeparator
+    nsgt, insgt = make_filterbanks(base)
+    T = 120 * 44100 + 77
+    x = torch.rand(1, 2, T, device=dev) * 2 - 1
+    gains = torch.tensor([0.9, 0.6, 0.4, 0.2], device=dev).view(4, 1, 1, 1, 1, 1, 1)
+    model = lambda X: [Xb.unsqueeze(0) * gains for Xb in X]
+    y_ref = insgt(model(nsgt(x)), T)
+    for chunk in (291, 37):
+        y = StreamedSeparator(base, model, chunk_slices=chunk)(x)
+        assert y.shape == (4, 1, 2, T)
+        assert torch.equal(y, y_ref), chunk

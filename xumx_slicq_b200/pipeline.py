@@ -86,3 +86,68 @@ class TransformStream:
         for pb, ph in pending:
             ev_out[ph].synchronize()
             yield self._yh[ph]
+
+
+class StreamedSeparator:
+    """Chunked demix of a long signal with overlap-exact stitching.
+
+    The reference's ``Separator.forward`` (separator.py:147-158,231) cuts the audio into independent chunks of
+    2 621 440 samples, zero-pads each chunk's edges inside the transform and concatenates the results: the slices
+    next to a chunk boundary see zeros instead of their neighbours' samples.  Here a chunk is a contiguous RANGE OF
+    SLICES of the one long transform -- the same decomposition as the multi-GPU slice sharding (sharding.py), run
+    sequentially in time on one GPU: the analysis of a chunk reads one hop of input before its first owned sample, and
+    the synthesis of a chunk hands the first half of its first slice back to the previous chunk's last hop.  For a
+    model that acts slice-locally (masks, phasemix) the concatenated output equals the unchunked
+    ``insgt(model(nsgt(x)), T)`` bit for bit; memory is bounded by the chunk, not by the track.
+
+        sep = StreamedSeparator(nsgt_base, model, chunk_slices=291)        # ~59 s like the reference's chunk
+        for lo, hi, y in sep.stream(x):   # x [B, C, T] on the device; y [targets, B, C, hi - lo] = samples lo .. hi
+            ...
+        y = sep(x)                        # the concatenation [targets, B, C, T]
+    """
+
+    def __init__(self, nsgt_base: NSGTBase, model: Callable[[List[torch.Tensor]], List[torch.Tensor]],
+                 chunk_slices: int = 291):
+        self.base = nsgt_base
+        self.nsgt, self.insgt = make_filterbanks(nsgt_base)
+        self.model = model
+        self.chunk = max(2, int(chunk_slices))
+
+    def stream(self, x: torch.Tensor) -> Iterator[tuple]:
+        nsg = self.base.nsgt
+        hop = nsg.sl_len // 2
+        lead, T = tuple(x.shape[:-1]), x.shape[-1]
+        x2 = x.reshape(-1, T)
+        S = nsg.n_slices(T)
+        prev = None                      # (lo, hi, y) of the previous chunk, waiting for its right neighbour's halo
+        for k0 in range(0, S, self.chunk):
+            k1 = min(S, k0 + self.chunk)
+            in_lo, own_lo, own_hi = max(0, (k0 - 1) * hop), min(T, k0 * hop), min(T, k1 * hop)
+            C = nsg.forward_rows(x2[:, in_lo:own_hi].contiguous(), k0=k0, n_slices=k1 - k0, t0=in_lo,
+                                 lead=lead, as_real=True)                      # wrapper layout [*lead, F, S_c, M, 2]
+            Y = self.model(C)
+            ylead = tuple(Y[0].shape[:-4])
+            rows = 1
+            for d in ylead:
+                rows *= d
+            views, keep = [], []
+            for Yb, (_, nb, M) in zip(Y, nsg.tables.buckets):
+                Yb = Yb.to(torch.float32).contiguous()
+                keep.append(Yb)
+                views.append((Yb.data_ptr(), nb * (k1 - k0) * M, (k1 - k0) * M, M))
+            halo = torch.zeros(rows, hop, dtype=torch.float32, device=x.device) if k0 > 0 else None
+            y = nsg.backward_views(views, rows, k1 - k0, x.device, own_hi - own_lo, k0=k0, t0=k0 * hop, halo_out=halo)
+            del keep
+            if prev is not None:
+                plo, phi, py = prev
+                a = (k0 - 1) * hop - plo                 # the previous chunk's last hop
+                n = max(0, py.shape[1] - a)
+                if n:
+                    py[:, a:a + n] += halo[:, :n]
+                yield plo, phi, py.view(*prev_lead, -1)
+            prev, prev_lead = (own_lo, own_hi, y), ylead
+        if prev is not None:
+            yield prev[0], prev[1], prev[2].view(*prev_lead, -1)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.cat([y for _, _, y in self.stream(x)], dim=-1)
