@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "xumx_slicq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libslicq_emu.so")
-SOURCES = ["slicq_api.cu", "k_bins.cu", "k_slice.cu"]
+SOURCES = ["slicq_api.cu", "k_bins.cu", "k_slice.cu", "k_slice_generic.cu"]
 
 
 def build_emu() -> str:
@@ -35,7 +35,7 @@ def build_emu() -> str:
                                "-c", os.path.join(CSRC, src), "-o", o])
         return o
 
-    with ThreadPoolExecutor(max_workers=3) as ex:
+    with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(cc, SOURCES))
     subprocess.check_call(["g++", "-shared", "-o", LIB] + objs)
     return LIB

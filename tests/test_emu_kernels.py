@@ -262,3 +262,28 @@ def test_streamed_separator_is_overlap_exact(base):
         y = sep(x)
         assert y.shape == y_ref.shape == (2, 1, 2, T)
         assert torch.equal(y, y_ref), chunk
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_other_configurations_vs_reference_golden(emu, golden_dir, idx):
+    """Bark(100, 50 Hz) (slice length 6884 = 4 * 1721, generic slice kernels) and tiny-mel
+    (mel, 32 bins, 115.5 Hz: slice length 2016, first bin below DC -> the reference's mirrored-bin pass matters) against
+    vectors generated by the unmodified reference (tests/golden/make_golden_alt.py)."""
+    from xumx_slicq_b200 import NSGTBase
+    gold = np.load(os.path.join(golden_dir, "alt_fwdinv.npz"))
+    name = str(gold[f"name{idx}"])
+    fb, fmin, sllen, T = gold[f"cfg{idx}"]
+    b = NSGTBase(name, int(fb), float(fmin), device="cpu")
+    assert b.sllen == int(sllen)
+    x = (np.random.RandomState(100 + idx).rand(2, int(T)).astype(np.float32) * 2 - 1)
+    buckets = [tuple(int(v) for v in bb) for bb in gold[f"buckets{idx}"]]
+    ref = common.unpack(gold[f"coefs{idx}"], buckets)
+    C = b.nsgt.forward((torch.from_numpy(x),))
+    assert len(C) == len(ref)
+    worst = max(rel_err(c.numpy(), r) for c, r in zip(C, ref))
+    assert worst < 1e-5, worst
+    y = b.nsgt.backward([torch.from_numpy(np.ascontiguousarray(r)) for r in ref], int(T)).numpy()
+    np.testing.assert_allclose(y, gold[f"y_roundtrip{idx}"], atol=5e-6)
+    P = common.perturb(ref)
+    yp = b.nsgt.backward([torch.from_numpy(p) for p in P], int(T)).numpy()
+    np.testing.assert_allclose(yp, gold[f"y_perturbed{idx}"], atol=5e-6)

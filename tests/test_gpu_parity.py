@@ -236,8 +236,8 @@ def test_error_paths(base, dev):
         make_filterbanks(base, sample_rate=48000.0)
     with pytest.raises(ValueError):
         base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64, device=dev)], 100)
-    with pytest.raises(ValueError):      # a Bark configuration whose slice length has no compiled kernel
-        NSGTBase("bark", 100, 50.0, device=dev).nsgt.plan()
+    with pytest.raises(ValueError):      # bin lengths beyond the compiled per-bin transforms (M up to 1664 here)
+        NSGTBase("cqlog", 48, 100.0, device=dev).nsgt.plan()
 
 
 def test_transform_stream_matches_direct_calls(base, dev):
@@ -440,3 +440,32 @@ def test_streamed_separator_overlap_exact(base, dev):
         y = StreamedSeparator(base, model, chunk_slices=chunk)(x)
         assert y.shape == (4, 1, 2, T)
         assert torch.equal(y, y_ref), chunk
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_other_configurations_vs_reference_golden(dev, golden_dir, idx):
+    """SURVEY section 8(f) N4 on the GPU: Bark(100, 50 Hz) (slice length 6884 = 4 * 1721: generic slice kernels) and
+    tiny-mel (mel, 32 bins, 115.5 Hz; slice length 2016; mirrored-bin pass) against reference-generated vectors."""
+    from xumx_slicq_b200 import NSGTBase
+    gold = np.load(os.path.join(golden_dir, "alt_fwdinv.npz"))
+    name = str(gold[f"name{idx}"])
+    fb, fmin, sllen, T = gold[f"cfg{idx}"]
+    b = NSGTBase(name, int(fb), float(fmin), device=dev)
+    assert b.sllen == int(sllen)
+    x = (np.random.RandomState(100 + idx).rand(2, int(T)).astype(np.float32) * 2 - 1)
+    buckets = [tuple(int(v) for v in bb) for bb in gold[f"buckets{idx}"]]
+    ref = common.unpack(gold[f"coefs{idx}"], buckets)
+    C = b.nsgt.forward((torch.from_numpy(x).to(dev),))
+    worst = max(rel_err(c.cpu().numpy(), r) for c, r in zip(C, ref))
+    assert worst < REL_TOL, worst
+    y = b.nsgt.backward([torch.from_numpy(np.ascontiguousarray(r)).to(dev) for r in ref], int(T)).cpu().numpy()
+    np.testing.assert_allclose(y, gold[f"y_roundtrip{idx}"], atol=5e-6)
+    P = common.perturb(ref)
+    yp = b.nsgt.backward([torch.from_numpy(p).to(dev) for p in P], int(T)).cpu().numpy()
+    np.testing.assert_allclose(yp, gold[f"y_perturbed{idx}"], atol=5e-6)
+    # a longer signal through the wrappers: round-trip SNR of the configuration
+    from xumx_slicq_b200 import make_filterbanks
+    nsgt, insgt = make_filterbanks(b)
+    xl = torch.rand(1, 2, 200000, device=dev) * 2 - 1
+    yl = insgt(nsgt(xl), xl.shape[-1])
+    assert snr_db(xl.cpu().numpy(), yl.cpu().numpy()) > 120.0

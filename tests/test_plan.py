@@ -75,4 +75,22 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         P.design(scl, 44100.0, 18060, 4515)   # odd transition (slicing.py:22-23)
     with pytest.raises(NotImplementedError):
-        P.make_scale("mel", 32.9, 22050.0, 262)
+        P.make_scale("mrstft", 32.9, 22050.0, 262)
+
+
+def test_other_scales_integer_tables(golden_dir):
+    """mel / cqlog / vqlog / linear (fscale.py:92-188, transforms.py:31-49) and more Bark
+    configurations give exactly the reference's slice length, bin lengths and bin positions."""
+    tab = np.load(os.path.join(golden_dir, "tables_scales.npz"))
+    i = 0
+    while f"cfg{i}" in tab:
+        name = str(tab[f"name{i}"])
+        fb, fmin = tab[f"cfg{i}"]
+        scl = P.make_scale(name, float(fmin), 22050.0, int(fb))
+        sllen, trlen = scl.suggested_sllen_trlen(44100.0)
+        t = P.design(scl, 44100.0, sllen, trlen)
+        assert [sllen, trlen, t.n_bins] == list(tab[f"sl{i}"]), (name, fb, fmin)
+        np.testing.assert_array_equal(t.M_all.astype(np.int64), tab[f"M{i}"], err_msg=f"{name} {fb} {fmin}")
+        np.testing.assert_array_equal(t.rfbas_all.astype(np.int64), tab[f"rfbas{i}"], err_msg=f"{name} {fb} {fmin}")
+        i += 1
+    assert i == 9

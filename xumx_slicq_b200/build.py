@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libslicq.so")
-SOURCES = ["slicq_api.cu", "k_bins.cu", "k_slice.cu"]
+SOURCES = ["slicq_api.cu", "k_bins.cu", "k_slice.cu", "k_slice_generic.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -419,9 +419,15 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
 }
 
 // host-side helpers / launchers ---------------------------------------------------------------
+extern "C" int slicq_generic_smem_bytes(int L);
+extern "C" int slicq_launch_slice_fwd_generic(const SlicqSliceParams* p, cudaStream_t s);
+extern "C" int slicq_launch_slice_inv_generic(const SlicqSliceParams* p, cudaStream_t s);
+
+// shared memory of the slice kernels for slice length L: the tuned prime-factor kernels for the pretrained
+// configuration, the generic kernels (k_slice_generic.cu) for every other length that fits; -1 = unsupported
 extern "C" int slicq_slice_smem_bytes(int L) {
     if (L == 2 * Pfa9030::N) return (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
-    return -1;
+    return slicq_generic_smem_bytes(L);
 }
 
 // cudaFuncSetAttribute is per device: remember which devices have the opt-in for > 48 KB dynamic shared memory
@@ -440,7 +446,7 @@ static int slice_attr(int smem) {
 
 extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
-    if (p->t.L != 2 * Pfa9030::N) return -2;
+    if (p->t.L != 2 * Pfa9030::N) return slicq_launch_slice_fwd_generic(p, s);
     const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     if (slice_attr(smem)) return -3;
     SLICQ_LAUNCH(slice_fft_fwd_kernel<Pfa9030>, dim3(p->n_rs), dim3(SLICQ_SLICE_THREADS), smem, s, *p);
@@ -449,7 +455,7 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s) {
     if (p->n_rs <= 0) return 0;
-    if (p->t.L != 2 * Pfa9030::N) return -2;
+    if (p->t.L != 2 * Pfa9030::N) return slicq_launch_slice_inv_generic(p, s);
     const int smem = (int)(Pfa9030::SMEM_ELEMS * sizeof(float2));
     if (slice_attr(smem)) return -3;
     // slices of parity q among units [0, u) of rows of S slices

@@ -56,6 +56,7 @@ extern "C" int slicq_launch_slice_fwd(const SlicqSliceParams* p, cudaStream_t s)
 extern "C" int slicq_launch_slice_inv(const SlicqSliceParams* p, cudaStream_t s);
 extern "C" int slicq_slice_smem_bytes(int L);
 extern "C" int slicq_bins_threads(void);
+extern "C" int slicq_launch_mirror_fix(const SlicqBinsParams* p, cudaStream_t s);
 
 namespace {
 
@@ -213,7 +214,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         return fail(SLICQ_E_INVALID, "missing tables");
     if (slicq_slice_smem_bytes(L) < 0) {
         char buf[160];
-        snprintf(buf, sizeof buf, "no slice-FFT kernel compiled for sl_len=%d (supported: 18060)", L);
+        snprintf(buf, sizeof buf, "slice length %d does not fit the slice kernels' shared memory (two buffers of sl_len/2 complex numbers)", L);
         return fail(SLICQ_E_UNSUPPORTED, buf);
     }
     slicq_plan* p = new slicq_plan();
@@ -236,12 +237,13 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         off += M;
     }
     p->sum_M = off;
-    // The reference also accumulates the conjugate mirror of bins 1..J-2 at L - pos_j
-    // (nsigtf.py:63-80).  The kernels drop that pass, valid only if it never reaches [0, L/2].
+    // The reference also accumulates a mirrored copy of bins 1..J-2 at L - pos_j (nsigtf.py:63-80).  It reaches the kept
+    // half spectrum [0, L/2] only from a bin that extends past Nyquist (unsupported) or below DC (handled by
+    // mirror_fix_kernel, entries built below).
     for (int j = 1; j < J - 1; ++j) {
-        if (L - p->bin_pos[j] - p->bin_M[j] / 2 <= p->N2) {
+        if (p->bin_pos[j] + p->bin_M[j] / 2 > p->N2) {
             delete p;
-            return fail(SLICQ_E_UNSUPPORTED, "a mirrored bin overlaps the kept half spectrum (unsupported scale)");
+            return fail(SLICQ_E_UNSUPPORTED, "a bin below Nyquist reaches beyond it: the mirrored-bin pass above Nyquist is not implemented");
         }
     }
     // buckets = maximal runs of equal M (nsgtf.py:66-78)
@@ -387,6 +389,37 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         }
     }
     if (gaps.empty()) gaps.push_back(int2{0, 0});
+    // mirrored-bin entries (see mirror_fix_kernel): bin j >= 1 with pos_j < M_j / 2; reference-order index m in [pos_j, M_j/2)
+    std::vector<SlicqMirrorEntry> mir;
+    for (size_t bi = 0; bi < p->buckets.size(); ++bi) {
+        const Bucket& b = p->buckets[bi];
+        for (int j = std::max(1, b.first_bin); j < std::min(J - 1, b.first_bin + b.n_bins); ++j) {
+            const int M = b.M, pos = p->bin_pos[j];
+            for (int m = pos; m < M / 2; ++m) {
+                const int f = m - pos;
+                if (f > N2) continue;
+                SlicqMirrorEntry e;
+                e.bucket = (int)bi; e.f_in_bucket = j - b.first_bin; e.m_src = m + 1; e.t_off = pl_off + f;
+                const double gdm = (double)t->win_inv[p->bin_coff[j] + (M - m) % M];      // dual window of the mirrored bin at m
+                const double sgn = (((pos / 2) + m) % 2) ? -1.0 : 1.0;                     // (-1)^(pos/2) (-1)^m
+                e.weight = (float)(sgn * gdm * (double)M / (double)L);
+                mir.push_back(e);
+            }
+        }
+    }
+    // (the adjoint-of-analysis plan has no such pass: the analysis reads the exact Hermitian mirror)
+    const int n_mir = (getenv("SLICQ_NO_MIRROR") || (t->flags & SLICQ_PLAN_ADJOINT_OF_ANALYSIS)) ? 0 : (int)mir.size();   // SLICQ_NO_MIRROR: verification aid (shows what the pass contributes)
+    if (mir.empty()) mir.push_back(SlicqMirrorEntry{0, 0, 0, 0, 0.f});
+    // generic slice kernels: prime factors of N2 (largest first) and the table exp(-2 pi i k / N2)
+    std::vector<int> fac;
+    { int n = N2; for (int d = 2; d * d <= n; ++d) while (n % d == 0) { fac.push_back(d); n /= d; } if (n > 1) fac.push_back(n); }
+    std::sort(fac.begin(), fac.end(), [](int x, int y) { return x > y; });
+    if (fac.size() > 20) { delete p; return fail(SLICQ_E_UNSUPPORTED, "too many prime factors in the slice length"); }
+    std::vector<float2> wN(N2);
+    for (int kk = 0; kk < N2; ++kk) {
+        const double ang = -2.0 * M_PI * (double)kk / (double)N2;
+        wN[kk] = make_float2((float)cos(ang), (float)sin(ang));
+    }
     SlicqDeviceTables& d = p->dev;
     memset(&d, 0, sizeof d);
     d.L = L; d.N2 = p->N2; d.hop = p->hop; d.n_bins = J; d.n_buckets = (int)p->buckets.size(); d.sum_M = p->sum_M;
@@ -408,6 +441,10 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(ovoff, &d.bin_ovoff, p->owned);
     rc |= upload(ex, &d.ex, p->owned);
     rc |= upload(gaps, &d.gaps, p->owned);
+    rc |= upload(mir, &d.mir, p->owned);
+    rc |= upload(wN, &d.wN, p->owned);
+    d.n_mir = n_mir; d.n_fac = (int)fac.size();
+    for (size_t i = 0; i < fac.size(); ++i) d.fac[i] = fac[i];
     d.n_ex = n_ex; d.pl_off = pl_off; d.pl_len = pl_len; d.t_stride = (int)p->t_stride;
     if (rc) {
         slicq_plan_destroy(p);
@@ -733,6 +770,7 @@ int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const sli
     SlicqBinsParams* bp = new SlicqBinsParams();
     bp->t = p->dev; bp->spec = T; bp->spec_stride = p->t_stride; bp->S = (int)n_slices;
     bp->x_rows = masks ? (int)x_rows : 0;
+    bp->k0 = (int)k0;
     SlicqSliceParams sp;
     memset(&sp, 0, sizeof sp);
     sp.t = p->dev; sp.k0 = k0; sp.spec = T; sp.spec_stride = p->t_stride; sp.S = (int)n_slices;
@@ -748,6 +786,11 @@ int inverse_one(const slicq_plan* p, const slicq_bucket_view* buckets, const sli
         { ProfScope ps(K_BINS_INV, s); rc = slicq_launch_bins(bp, jobs, p->bins_smem, 1, s); }
         ++g_launches;
         if (rc) break;
+        if (p->dev.n_mir > 0) {          // mirrored-bin pass of configurations whose first bins reach below DC
+            rc = slicq_launch_mirror_fix(bp, s);
+            ++g_launches;
+            if (rc) break;
+        }
         sp.n_rs = (int)n; sp.rs0 = (int)u0;
         {
             ProfScope ps(K_SLICE_INV, s);

@@ -125,6 +125,9 @@ SLICQ_DEVFN float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
 SLICQ_DEVFN float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // ---------------------------------------------------------------------------------------
+// mirrored-bin pass of the reference (nsigtf.py:63-80) for a bin that reaches below DC: one entry per spectrum position
+struct SlicqMirrorEntry { int bucket, f_in_bucket, m_src, t_off; float weight; };
+
 // device-side tables owned by the plan (all in global memory, < 1 MB, L2 resident)
 struct SlicqDeviceTables {
     int L;          // slice length (sl_len)
@@ -161,6 +164,12 @@ struct SlicqDeviceTables {
     const int4* ex;               // [n_ex] {f, off0, off1 or -1, 0}: position f also receives T[off0] (+ T[off1])
     int n_ex;
     const int2* gaps;             // {offset in the row, count}: zero-filled per unit by the job of the owning bucket
+    // generic slice kernels (k_slice_generic.cu): prime factors of N2 and exp(-2 pi i k / N2)
+    int n_fac;
+    int fac[20];
+    const float2* wN;
+    const SlicqMirrorEntry* mir;  // [n_mir]
+    int n_mir;
 };
 
 // one bucket as a kernel sees it for one call (pointer + strides of the caller's tensor)
@@ -196,7 +205,7 @@ struct SlicqBinsParams {
     int S;                 // slices per row in this call
     int n_buckets;
     int x_rows;            // masked synthesis: rows of the mixture tensor (output row r reads mixture row r % x_rows); else 0
-    int pad_;
+    int k0;                // global index of local slice 0 (slice parity for the mirrored-bin pass)
     SlicqBucketArg b[SLICQ_MAX_BUCKETS];
 };
 

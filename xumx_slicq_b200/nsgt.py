@@ -406,6 +406,10 @@ class NSGT_sliced(torch.nn.Module):
         <y, g> = sum y*g, <c, d> = sum Re(c) Re(d) + Im(c) Im(d).  Runs on the analysis kernels
         with a second plan (no slicing window, dual windows, zero instead of mirrored margins)."""
         _BACKEND.check(g)
+        t = self.tables
+        if any(int(t.bin_pos[j]) < int(t.bin_M[j]) // 2 for j in range(1, t.n_bins - 1)):
+            raise NotImplementedError("gradients through the synthesis are not implemented for configurations whose "
+                                      "bins reach below DC (the reference's mirrored-bin pass has no adjoint kernel here)")
         if self._adj_tables is None:
             self._adj_tables = _AdjointTables(self.tables)
         if g.dtype != torch.float32:

@@ -24,22 +24,20 @@ F32 = np.float32
 
 
 # ---------------------------------------------------------------------------- frequency scales
-class BarkScale:
-    """Bark frequency scale, fscale.py:56-89; Q by central difference, fscale.py:15-23."""
+class Scale:
+    """fscale.py:5-53: a scale maps band index -> frequency F(b); Q(b) defaults to the central difference
+    F dbnd / (F(b + dbnd) - F(b - dbnd)); (f, q) are float32 like the reference's tensors."""
 
     _DB = 1.0e-8
 
-    def __init__(self, fmin: float, fmax: float, bnds: int, device=None):
-        self.fmin, self.fmax, self.bnds = float(fmin), float(fmax), int(bnds)
-        lo, hi = 6.0 * math.asinh(fmin / 600.0), 6.0 * math.asinh(fmax / 600.0)
-        self._step = (hi - lo) / (bnds - 1)
-        self._lo = lo
+    def __init__(self, bnds: int):
+        self.bnds = int(bnds)
 
     def __len__(self):
         return self.bnds
 
     def F(self, bnd):
-        return 600.0 * math.sinh((bnd * self._step + self._lo) / 6.0)
+        raise NotImplementedError
 
     def Q(self, bnd):
         return self.F(bnd) * self._DB / (self.F(bnd + self._DB) - self.F(bnd - self._DB))
@@ -59,12 +57,84 @@ class BarkScale:
         return sllen, trlen
 
 
+class BarkScale(Scale):
+    """Bark frequency scale, fscale.py:56-89; Q by central difference, fscale.py:15-23."""
+
+    def __init__(self, fmin: float, fmax: float, bnds: int, device=None):
+        super().__init__(bnds)
+        self.fmin, self.fmax = float(fmin), float(fmax)
+        lo, hi = 6.0 * math.asinh(fmin / 600.0), 6.0 * math.asinh(fmax / 600.0)
+        self._step = (hi - lo) / (bnds - 1)
+        self._lo = lo
+
+    def F(self, bnd):
+        return 600.0 * math.sinh((bnd * self._step + self._lo) / 6.0)
+
+
+class MelScale(Scale):
+    """fscale.py:131-166 (Q by central difference: the reference's Q1 is not used)."""
+
+    def __init__(self, fmin: float, fmax: float, bnds: int):
+        super().__init__(bnds)
+        self.fmin, self.fmax = float(fmin), float(fmax)
+        mmin, mmax = math.log10(fmin / 700.0 + 1.0) * 2595.0, math.log10(fmax / 700.0 + 1.0) * 2595.0
+        self.mbnd = (mmax - mmin) / (bnds - 1)
+        self.mmin = mmin
+
+    def F(self, bnd):
+        return (math.pow(10.0, (bnd * self.mbnd + self.mmin) / 2595.0) - 1.0) * 700.0
+
+
+class LogScale(Scale):
+    """fscale.py:92-128: constant-Q ("cqlog", gamma = 0) and variable-Q with offset ("vqlog", gamma = fgamma)."""
+
+    def __init__(self, fmin: float, fmax: float, bnds: int, gamma: float = 0.0):
+        super().__init__(bnds)
+        lfmin, lfmax = math.log2(fmin), math.log2(fmax)
+        odiv = (lfmax - lfmin) / (bnds - 1)
+        self.fmin, self.fmax = 2 ** lfmin, 2 ** lfmax
+        self.pow2n = 2 ** odiv
+        self.q = math.sqrt(self.pow2n) / (self.pow2n - 1.0) / 2.0
+        self.gamma = float(gamma)
+
+    def F(self, bnd):
+        return self.fmin * self.pow2n ** bnd + self.gamma
+
+    def Q(self, bnd):
+        return self.q
+
+
+class LinScale(Scale):
+    """fscale.py:169-188."""
+
+    def __init__(self, fmin: float, fmax: float, bnds: int):
+        super().__init__(bnds)
+        self.df = float(fmax - fmin) / (bnds - 1)
+        self.fmin, self.fmax = float(fmin), float(fmax)
+        if self.fmin <= 0:
+            raise ValueError("Frequencies must be > 0.")
+
+    def F(self, bnd):
+        return bnd * self.df + self.fmin
+
+    def Q(self, bnd):
+        return self.F(bnd) / (self.df * 2)
+
+
 def make_scale(name: str, fmin: float, fmax: float, fbins: int, fgamma: float = 15.0):
+    """transforms.py:31-49."""
     if name == "bark":
         return BarkScale(fmin, fmax, fbins)
+    if name == "mel":
+        return MelScale(fmin, fmax, fbins)
+    if name == "cqlog":
+        return LogScale(fmin, fmax, fbins)
+    if name == "vqlog":
+        return LogScale(fmin, fmax, fbins, gamma=fgamma)
+    if name == "linear":
+        return LinScale(fmin, fmax, fbins)
     raise NotImplementedError(
-        f"scale '{name}': only the Bark scale of the pretrained xumx-sliCQ-V2 models is built "
-        "(north star); mel/cqlog/vqlog/linear/mrstft are listed as 'next' in DESIGN.md")
+        f"scale '{name}': bark, mel, cqlog, vqlog and linear are built; the reference's 576-band 'mrstft' scale is not")
 
 
 # ---------------------------------------------------------------------------- windows
