@@ -468,4 +468,9 @@ def test_other_configurations_vs_reference_golden(dev, golden_dir, idx):
     nsgt, insgt = make_filterbanks(b)
     xl = torch.rand(1, 2, 200000, device=dev) * 2 - 1
     yl = insgt(nsgt(xl), xl.shape[-1])
-    assert snr_db(xl.cpu().numpy(), yl.cpu().numpy()) > 120.0
+    # tiny-mel: the reference's mirrored-bin pass (conj(cat(t[1:], flip(t[1:])))) is not the exact Hermitian mirror, so the
+    # reference itself reconstructs this configuration to ~99 dB only; we reproduce that (golden parity above)
+    assert snr_db(xl.cpu().numpy(), yl.cpu().numpy()) > (120.0 if idx == 0 else 95.0)
+    xs = x[:, :int(T)]
+    ours, theirs = snr_db(xs, y), snr_db(xs, gold[f"y_roundtrip{idx}"])
+    assert abs(ours - theirs) < SNR_SLACK_DB, (ours, theirs)
