@@ -473,4 +473,4 @@ def test_other_configurations_vs_reference_golden(dev, golden_dir, idx):
     assert snr_db(xl.cpu().numpy(), yl.cpu().numpy()) > (120.0 if idx == 0 else 95.0)
     xs = x[:, :int(T)]
     ours, theirs = snr_db(xs, y), snr_db(xs, gold[f"y_roundtrip{idx}"])
-    assert abs(ours - theirs) < SNR_SLACK_DB, (ours, theirs)
+    assert ours > theirs - SNR_SLACK_DB, (ours, theirs)       # not worse than the reference (better is fine)

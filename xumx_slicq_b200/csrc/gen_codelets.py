@@ -532,12 +532,6 @@ def generate() -> str:
             parts.append("}\n")
     for (p, nparts) in PRIME_PARTS:
         parts.extend(gen_prime_parts(p, nparts))
-    for p in REAL_SYM_PRIMES:
-        body, flops = gen_real_sym(p)
-        parts.append(f"// real symmetric half-DFT, prime {p}: {flops} flops")
-        parts.append(f"template <> SLICQ_DEVFN void rdft_sym<{p}>(const float (&x)[{p}], float* out, int stride) {{")
-        parts.extend(body)
-        parts.append("}\n")
     return "\n".join(parts)
 
 

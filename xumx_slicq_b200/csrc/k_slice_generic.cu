@@ -29,13 +29,29 @@ SLICQ_DEVFN float2* stockham(float2* x, float2* y, const SlicqDeviceTables& t) {
             const float2* src = x + r + s * q;
             float2 acc = src[0];
             int jk = 0;
-            for (int k = 1; k < pf; ++k) {
-                jk += j; if (jk >= pf) jk -= pf;
-                float2 w = __ldg(t.wN + wp * jk);
-                if (INV) w.y = -w.y;
-                const float2 a = src[s * m * k];
-                acc.x += a.x * w.x - a.y * w.y;
-                acc.y += a.x * w.y + a.y * w.x;
+            if (pf <= 32 || st != 0) {       // only the largest factor (first stage) has a double table
+                for (int k = 1; k < pf; ++k) {
+                    jk += j; if (jk >= pf) jk -= pf;
+                    float2 w = __ldg(t.wN + wp * jk);
+                    if (INV) w.y = -w.y;
+                    const float2 a = src[s * m * k];
+                    acc.x += a.x * w.x - a.y * w.y;
+                    acc.y += a.x * w.y + a.y * w.x;
+                }
+            } else {
+                // a large prime factor (e.g. 1721 for sl_len 6884) is a direct sum of pf terms: accumulate in double so that
+                // the transform keeps the accuracy of an FFT (round-trip SNR within 0.1 dB of the reference)
+                // (double twiddles too: fp32 twiddle rounding alone would add sqrt(pf) * 6e-8 of noise)
+                double ax = acc.x, ay = acc.y;
+                for (int k = 1; k < pf; ++k) {
+                    jk += j; if (jk >= pf) jk -= pf;
+                    double2 w = t.wP[jk];
+                    if (INV) w.y = -w.y;
+                    const float2 a = src[s * m * k];
+                    ax += (double)a.x * w.x - (double)a.y * w.y;
+                    ay += (double)a.x * w.y + (double)a.y * w.x;
+                }
+                acc = make_float2((float)ax, (float)ay);
             }
             float2 tw = __ldg(t.wN + wn * j * q);
             if (INV) tw.y = -tw.y;

@@ -112,14 +112,14 @@ int fft_smem_per_transform(const FftPlan& f) {
         const int a = f.A * bp, b = f.B * ap;
         return (a > b ? a : b) * 8;
     }
-    return f.M * 8;  // kind 3: R * 2 * P floats
+    return (f.M + f.A) * 8;  // kind 3: [R][P] (synthesis) / [P][R + 1] (analysis) complex
 }
 
 // threads one transform occupies in the pass whose per-thread state is hoisted out of the unit loop
 int fft_threads_per_transform(const FftPlan& f) {
     if (f.kind == 1) return 1;
     if (f.kind == 2) return f.B;
-    return 2 * f.B;  // kind 3: (n2, re|im)
+    return f.B * (f.A <= 41 ? 2 : (f.A <= 61 ? 3 : 4));  // kind 3: (part, n2): the DFT-P is split by outputs over 2-4 threads
 }
 
 struct Bucket {
@@ -342,7 +342,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     // two-pass / prime transforms store their first run of A outputs through one select: the overflow part must fit
     for (const Bucket& b : p->buckets)
         for (int j = b.first_bin; j < b.first_bin + b.n_bins; ++j)
-            if (b.kind != 1 && ov[j] > b.A) { delete p; return fail(SLICQ_E_UNSUPPORTED, "overlap between bins of one plane exceeds the first transform pass"); }
+            if ((b.kind == 2 && ov[j] > b.A) || (b.kind == 3 && ov[j] > b.B)) { delete p; return fail(SLICQ_E_UNSUPPORTED, "overlap between bins of one plane exceeds the first transform pass"); }
     p->t_stride = (2LL * pl_len + n_ovf + 1) & ~1LL;
     std::vector<int4> ex;
     {
@@ -415,6 +415,11 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     { int n = N2; for (int d = 2; d * d <= n; ++d) while (n % d == 0) { fac.push_back(d); n /= d; } if (n > 1) fac.push_back(n); }
     std::sort(fac.begin(), fac.end(), [](int x, int y) { return x > y; });
     if (fac.size() > 20) { delete p; return fail(SLICQ_E_UNSUPPORTED, "too many prime factors in the slice length"); }
+    std::vector<double2> wP(fac[0] > 32 ? fac[0] : 1);
+    for (size_t kk = 0; kk < wP.size(); ++kk) {
+        const double ang = -2.0 * M_PI * (double)kk / (double)wP.size();
+        wP[kk].x = cos(ang); wP[kk].y = sin(ang);
+    }
     std::vector<float2> wN(N2);
     for (int kk = 0; kk < N2; ++kk) {
         const double ang = -2.0 * M_PI * (double)kk / (double)N2;
@@ -443,6 +448,7 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     rc |= upload(gaps, &d.gaps, p->owned);
     rc |= upload(mir, &d.mir, p->owned);
     rc |= upload(wN, &d.wN, p->owned);
+    rc |= upload(wP, &d.wP, p->owned);
     d.n_mir = n_mir; d.n_fac = (int)fac.size();
     for (size_t i = 0; i < fac.size(); ++i) d.fac[i] = fac[i];
     d.n_ex = n_ex; d.pl_off = pl_off; d.pl_len = pl_len; d.t_stride = (int)p->t_stride;
@@ -456,9 +462,9 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
     if (mb < 1) mb = 1;
     p->chunk_bytes = mb << 20;
     const char* envj = getenv("SLICQ_BINS_JOBS");
-    // jobs per bins launch: 148 SMs x 3 resident CTAs x 5 waves for large launches (short jobs even out the tail;
-    // swept 666 ... 8880 at batch 8), 1184 for small ones (a job keeps enough iterations to amortise its set-up);
-    // SLICQ_BINS_JOBS fixes the number
+    // jobs per bins launch: 148 SMs x 3 resident CTAs x 10 waves for large launches (short jobs even out the tail;
+    // swept 666 ... 8880 at batch 8 in both rounds), 1184 for small ones (a job keeps enough iterations to amortise its
+    // set-up); SLICQ_BINS_JOBS fixes the number
     p->target_jobs = envj ? atoi(envj) : 0;
     if (p->target_jobs < 0) p->target_jobs = 0;
     const char* envs = getenv("SLICQ_SPLIT_UNITS");
@@ -549,7 +555,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
     bp.n_buckets = (int)p->buckets.size();
     double total = 0.0;
     for (const Bucket& b : p->buckets) total += b.cost;
-    const int target = p->target_jobs > 0 ? p->target_jobs : std::min(2220, std::max(1184, n_rs / 2));
+    const int target = p->target_jobs > 0 ? p->target_jobs : std::min(4440, std::max(1184, n_rs));
     for (size_t i = 0; i < p->buckets.size(); ++i) {
         const Bucket& b = p->buckets[i];
         SlicqBucketArg& a = bp.b[i];

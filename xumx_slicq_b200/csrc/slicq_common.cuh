@@ -21,6 +21,7 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
+struct double2 { double x, y; };
 static inline int2 make_int2(int a, int b) { int2 r; r.x = a; r.y = b; return r; }
 static inline int4 make_int4(int a, int b, int c, int d) { int4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
@@ -168,6 +169,7 @@ struct SlicqDeviceTables {
     int n_fac;
     int fac[20];
     const float2* wN;
+    const double2* wP;            // exp(-2 pi i k / fac[0]) in double when the largest factor is > 32 (direct sums of many terms)
     const SlicqMirrorEntry* mir;  // [n_mir]
     int n_mir;
 };

@@ -401,23 +401,52 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
 // =========================================================================================
 // kind 3 : M = P * R, P prime >= 29, R in {4, 8}
 // =========================================================================================
+// The DFT-P is the streamed symmetric direct form split BY OUTPUTS over NP threads (Dftp<P, NP>, gen_codelets.py):
+// packed complex FFMA2 with immediate twiddles, the accumulators the only long-lived registers.  The centring sign
+// (-1)^n splits over the two index parts: a compile-time rotation by R/2 of the DFT-R side and a sign folded into the
+// job's twiddle table.
+template <int M> struct PrimeSrcSyn {      // synthesis pass 2: column n2 = 0 .. P-1, contiguous in shared memory
+    const float2* p;
+    SLICQ_DEVFN cpx ld(int n) const { return cpx_ld(p + n); }
+};
+struct PrimeSrcAna {                       // analysis pass 1: x'[R n + n2] * window, straight from the padded spectrum
+    const float2* p; const float* w; int R;
+    SLICQ_DEVFN cpx ld(int n) const { return cmulr(cpx_ld(p + R * n), w[R * n]); }
+};
+struct PrimeDstSyn {                       // synthesis pass 2: output k2 -> T[base + R k2] * window
+    float2* o; const float* w; int R; int ovd;    // ovd: offset of the overflow slot relative to the plane slot, 0 = none
+    SLICQ_DEVFN void st(int k, cpx v) const { cpx_st(o + R * k + (k == 0 ? ovd : 0), cmulr(v, w[R * k])); }
+};
+struct PrimeDstAna {                       // analysis pass 1: output k1 -> stage[k1 * RP + n2] * twiddle
+    float2* o; const float2* tw; int RP, R;
+    SLICQ_DEVFN void st(int k, cpx v) const { cpx_st(o + RP * k, k == 0 ? v : cmulw(v, tw[R * k])); }
+};
+constexpr __host__ __device__ int prime_parts(int P) { return P <= 41 ? 2 : (P <= 61 ? 3 : 4); }   // gen_codelets.py PRIME_PARTS
+
 // analysis (prime first): x'[R*n1 + n2], n1 in [0,P) -> X[k1 + P*k2]
 template <int M, int P, int R>
-SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* sm) {
-    static_assert(P * R == M, "bad split");
-    constexpr int H = (P - 1) / 2;
+SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* smf) {
+    static_assert(P * R == M && R % 2 == 0, "bad split");
+    constexpr int NP = (P <= 41 ? 2 : (P <= 61 ? 3 : 4)), RP = R + 1, PER = P * RP;
+    typedef Dftp<P, NP, true> D;
     const int tid = threadIdx.x;
-    long long* so = reinterpret_cast<long long*>(sm);
-    sm += SLICQ_SLOT_BYTES / sizeof(float);
-    // job twiddles as [n2][k1], the bucket's analysis windows (its bins are contiguous in wf) and the
-    // spectrum offset of each bin in shared memory behind the stage
-    float2* twsm = reinterpret_cast<float2*>(sm + (size_t)j.gt * j.F * M * 2);
+    long long* so = reinterpret_cast<long long*>(smf);
+    float2* sm = reinterpret_cast<float2*>(smf + SLICQ_SLOT_BYTES / sizeof(float));
+    // job twiddles [k1][n2] = conj(exp(-2 pi i n2 k1 / M)) (-1)^k1, the bucket's analysis windows and the spectrum offset of
+    // each bin in shared memory behind the stage
+    float2* twsm = sm + (size_t)j.gt * j.F * PER;
     float* wsm = reinterpret_cast<float*>(twsm + M);
     int* hoff = reinterpret_cast<int*>(wsm + j.F * M);
     {
         const float2* __restrict__ tw = p.t.tw + b.tw_off;
         const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
-        for (int t = tid; t < M; t += blockDim.x) { const int c2 = t / P, k1 = t - c2 * P; twsm[t] = __ldg(tw + c2 * k1); }
+        for (int t = tid; t < M; t += blockDim.x) {
+            const int k1 = t / R, c2 = t - k1 * R;
+            float2 w = __ldg(tw + c2 * k1);
+            w.y = -w.y;
+            if (k1 & 1) { w.x = -w.x; w.y = -w.y; }
+            twsm[t] = w;
+        }
         for (int t = tid; t < j.F * M; t += blockDim.x) wsm[t] = __ldg(p.t.wf + coff_first + t);
         for (int t = tid; t < j.F; t += blockDim.x) hoff[t] = p.t.pad_l + __ldg(p.t.bin_pos + j.first_bin + t) - M / 2;
     }
@@ -425,48 +454,37 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
     for (int base = j.u0; base < j.u1; base += j.gt) {
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
-        // pass 1: real symmetric half transforms, task = (unit, bin, n2, re|im)
-        for (int t = tid; t < ng * j.F * R * 2; t += blockDim.x) {
-            const int c = t & 1, u = t >> 1;
-            const int slot = u / R, n2 = u - slot * R;
-            const int gs = slot / j.F, f = slot - gs * j.F;
-            const float* wv = wsm + f * M + n2;
-            const float* h = reinterpret_cast<const float*>(p.spec + (long long)(base + gs) * p.spec_stride + hoff[f] + n2) + c;
-            float x[P];
-#pragma unroll
-            for (int n1 = 0; n1 < P; ++n1) x[n1] = h[2 * R * n1] * wv[R * n1];
-            rdft_sym<P>(x, sm + (size_t)(u * 2 + c) * P, 1);
+        // pass 1: DFT-P, task = (part, slot, n2 < R); a part's tasks fill whole warps
+        const int ncol = ng * j.F * R, colp = (ncol + 31) & ~31;
+        for (int t = tid; t < NP * colp; t += blockDim.x) {
+            const int part = t / colp, c = t - part * colp;
+            if (c >= ncol) continue;
+            const int s = c / R, c2 = c - s * R;
+            const int gs = s / j.F, f = s - gs * j.F;
+            PrimeSrcAna src;
+            src.p = p.spec + (long long)(base + gs) * p.spec_stride + hoff[f] + c2;
+            src.w = wsm + f * M + c2; src.R = R;
+            cpx o[D::NOUT];
+            D::run(part, src, o);
+            PrimeDstAna dst; dst.o = sm + s * PER + c2; dst.tw = twsm + c2; dst.RP = RP; dst.R = R;
+            D::store(part, dst, o);
         }
         __syncthreads();
-        // pass 2: combine (inverse direction), twiddle, DFT-R, store runs of P
+        // pass 2: DFT-R with its inputs rotated by R/2 ((-1)^k2 on the outputs, P odd), runs of P to the caller's tensor
         for (int t = tid; t < ng * j.F * P; t += blockDim.x) {
-            const int slot = t / P, k1 = t - slot * P;
-            const int kk = k1 <= H ? k1 : P - k1;
-            const bool minus = k1 > H;       // inverse: X[kk] = (Ar - Bi, Ai + Br), X[P-kk] = (Ar + Bi, Ai - Br)
-            const bool odd = k1 & 1;
-            float2 v[R];
+            const int s = t / P, k1 = t - s * P;
+            const float2* src = sm + s * PER + k1 * RP;
+            cpx v[R];
 #pragma unroll
-            for (int n2 = 0; n2 < R; ++n2) {
-                const float* re = sm + (size_t)((slot * R + n2) * 2) * P;
-                const float* im = re + P;
-                float2 y = make_float2(re[kk], im[kk]);
-                if (k1 != 0) {
-                    float br = re[P - kk], bi = im[P - kk];
-                    if (minus) { br = -br; bi = -bi; }
-                    y.x -= bi;
-                    y.y += br;
-                }
-                if (n2 != 0 && k1 != 0) y = cmul_conj(y, twsm[n2 * P + k1]);
-                v[n2] = cneg_if(y, odd);
-            }
+            for (int n = 0; n < R; ++n) v[n] = cpx_ld(src + (n + R / 2) % R);
             dft<R, true>(v);
-            float2* o = b.ptr + so[slot] + k1;
+            float2* o = b.ptr + so[s] + k1;
 #pragma unroll
-            for (int k2 = 0; k2 < R; ++k2) o[P * k2] = cneg_if(v[k2], k2 & 1);   // P odd: (-1)^(P k2) = (-1)^k2
+            for (int k2 = 0; k2 < R; ++k2) cpx_st(o + P * k2, v[k2]);
             if (b.nptr != nullptr) {
-                float* on = b.nptr + so[256 + slot] + k1;
+                float* on = b.nptr + so[256 + s] + k1;
 #pragma unroll
-                for (int k2 = 0; k2 < R; ++k2) on[P * k2] = cmag(v[k2]);
+                for (int k2 = 0; k2 < R; ++k2) on[P * k2] = cmag(cpx_to(v[k2]));
             }
         }
         __syncthreads();
@@ -475,22 +493,27 @@ SLICQ_DEVFN void ana_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
 
 // synthesis (prime last): x[P*n1 + n2], n1 in [0,R) -> X[k1 + R*k2], k2 in [0,P)
 template <int M, int P, int R>
-SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* sm) {
-    static_assert(P * R == M, "bad split");
-    constexpr int H = (P - 1) / 2;
+SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, const JobCtx& j, float* smf) {
+    static_assert(P * R == M && R % 2 == 0, "bad split");
+    constexpr int NP = (P <= 41 ? 2 : (P <= 61 ? 3 : 4));
+    typedef Dftp<P, NP, false> D;
     const int tid = threadIdx.x;
-    long long* so = reinterpret_cast<long long*>(sm);
-    sm += SLICQ_SLOT_BYTES / sizeof(float);
-    // job twiddles transposed to [k1][n2] and the bucket's dual windows (its bins are contiguous in wi
-    // and in the packed row T) in shared memory behind the stage
-    float2* twsm = reinterpret_cast<float2*>(sm + (size_t)j.gt * j.F * M * 2);
+    long long* so = reinterpret_cast<long long*>(smf);
+    float2* sm = reinterpret_cast<float2*>(smf + SLICQ_SLOT_BYTES / sizeof(float));
+    // job twiddles [k1][n2] = exp(-2 pi i n2 k1 / M) (-1)^n2, the bucket's dual windows and the T-row offsets of its bins
+    float2* twsm = sm + (size_t)j.gt * j.F * (M + P);
     float* wsm = reinterpret_cast<float*>(twsm + M);
     const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
     const int FM = j.F * M;
     int* tob = reinterpret_cast<int*>(wsm + FM);           // [F] {offset of m' = 0 in the T row, overflow count, overflow offset}
     {
         const float2* __restrict__ tw = p.t.tw + b.tw_off;
-        for (int t = tid; t < M; t += blockDim.x) { const int k1 = t / P, c2 = t - k1 * P; twsm[t] = __ldg(tw + c2 * k1); }
+        for (int t = tid; t < M; t += blockDim.x) {
+            const int k1 = t / P, c2 = t - k1 * P;
+            float2 w = __ldg(tw + c2 * k1);
+            if (c2 & 1) { w.x = -w.x; w.y = -w.y; }
+            twsm[t] = w;
+        }
         for (int t = tid; t < FM; t += blockDim.x) wsm[t] = __ldg(p.t.wi + coff_first + t);
         for (int t = tid; t < j.F; t += blockDim.x) {
             tob[3 * t] = __ldg(p.t.bin_toff + j.first_bin + t);
@@ -502,63 +525,40 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
         const int ng = (j.u1 - base < j.gt) ? (j.u1 - base) : j.gt;
         fill_slot_off(so, b, j, base, ng);
         __syncthreads();
-        // pass 1: DFT-R + twiddle, task = (unit, bin, n2), input runs of P from HBM
+        // pass 1: DFT-R, task = (slot, n2 < P), input runs of P from the caller's tensor; (-1)^n1 = outputs rotated by R/2
         for (int t = tid; t < ng * j.F * P; t += blockDim.x) {
-            const int slot = t / P, n2 = t - slot * P;
-            const float2* src = b.ptr + so[slot] + n2;
-            const bool odd = n2 & 1;
-            float2 v[R];
+            const int s = t / P, c2 = t - s * P;
+            const float2* src = b.ptr + so[s] + c2;
+            cpx v[R];
 #pragma unroll
-            for (int n1 = 0; n1 < R; ++n1) v[n1] = cneg_if(src[P * n1], odd != ((n1 & 1) != 0));  // (-1)^(P n1 + n2)
+            for (int n1 = 0; n1 < R; ++n1) v[n1] = cpx_ld(src + P * n1);
             if (b.mptr != nullptr) {
-                const float* msrc = b.mptr + so[256 + slot] + n2;
+                const float* msrc = b.mptr + so[256 + s] + c2;
 #pragma unroll
-                for (int n1 = 0; n1 < R; ++n1) v[n1] = cscale(v[n1], msrc[P * n1]);
+                for (int n1 = 0; n1 < R; ++n1) v[n1] = cmulr(v[n1], msrc[P * n1]);
             }
             dft<R, false>(v);
+            float2* o = sm + s * (M + P) + c2;
+            const float2* twp = twsm + c2;
 #pragma unroll
-            for (int k1 = 0; k1 < R; ++k1) {
-                float2 y = v[k1];
-                if (k1 != 0 && n2 != 0) y = cmul(y, twsm[k1 * P + n2]);
-                float* re = sm + (size_t)((slot * R + k1) * 2) * P;
-                re[n2] = y.x;
-                re[P + n2] = y.y;
-            }
+            for (int k1 = 0; k1 < R; ++k1) cpx_st(o + k1 * P, cmulw(v[(k1 + R / 2) % R], twp[k1 * P]));
         }
         __syncthreads();
-        // pass 2a: real symmetric half transforms in place
-        for (int t = tid; t < ng * j.F * R * 2; t += blockDim.x) {
-            float* row = sm + (size_t)t * P;
-            float x[P];
-#pragma unroll
-            for (int n = 0; n < P; ++n) x[n] = row[n];
-            rdft_sym<P>(x, row, 1);
-        }
-        __syncthreads();
-        // pass 2b: combine (forward direction), dual window, store: element e of the unit's contiguous
-        // bucket block [coff_first, coff_first + F*M); e advances by blockDim <= F*M (M >= 116 for these sizes)
-        {
-            int gs = 0, e = tid;
-            while (e >= FM) { e -= FM; ++gs; }
-            while (gs < ng) {
-                const int f = e / M, r = e - f * M;
-                const int k2 = r / R, k1 = r - k2 * R;
-                const int kk = k2 <= H ? k2 : P - k2;
-                const float* re = sm + (size_t)(((gs * j.F + f) * R + k1) * 2) * P;
-                const float* im = re + P;
-                float2 y = make_float2(re[kk], im[kk]);
-                if (k2 != 0) {
-                    float br = re[P - kk], bi = im[P - kk];
-                    if (k2 > H) { br = -br; bi = -bi; }   // forward: X[kk] = (Ar + Bi, Ai - Br), X[P-kk] = (Ar - Bi, Ai + Br)
-                    y.x += bi;
-                    y.y -= br;
-                }
-                const float wv = wsm[e];
-                const int off = (r < tob[3 * f + 1] ? tob[3 * f + 2] : tob[3 * f]) + r;
-                p.spec[SLICQ_TROW(base + gs) * p.spec_stride + off] = make_float2(y.x * wv, y.y * wv);
-                e += blockDim.x;
-                while (e >= FM) { e -= FM; ++gs; }
-            }
+        // pass 2: DFT-P, task = (part, slot, k1); dual window, runs of R outputs to the plane row
+        const int ncol = ng * j.F * R, colp = (ncol + 31) & ~31;
+        for (int t = tid; t < NP * colp; t += blockDim.x) {
+            const int part = t / colp, c = t - part * colp;
+            if (c >= ncol) continue;
+            const int s = c / R, k1 = c - s * R;
+            const int gs = s / j.F, f = s - gs * j.F;
+            PrimeSrcSyn<M> src; src.p = sm + s * (M + P) + k1 * P;
+            cpx o[D::NOUT];
+            D::run(part, src, o);
+            PrimeDstSyn dst;
+            dst.o = p.spec + SLICQ_TROW(base + gs) * p.spec_stride + tob[3 * f] + k1;
+            dst.w = wsm + f * M + k1; dst.R = R;
+            dst.ovd = (k1 < tob[3 * f + 1]) ? tob[3 * f + 2] - tob[3 * f] : 0;
+            D::store(part, dst, o);
         }
         __syncthreads();
     }
