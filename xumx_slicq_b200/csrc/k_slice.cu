@@ -58,7 +58,11 @@ struct PfaNat {
     static_assert(SA >= P2 * SB && SB >= P3, "pitches too small");
     static_assert(NP * SLOT <= SLICQ_SLICE_THREADS, "pass A needs NP * SLOT threads");
 };
-typedef PfaNat<43, 15, 14, 2, 16, 243> Pfa9030;
+#ifndef SLICQ_PFA_SB
+#define SLICQ_PFA_SB 16
+#define SLICQ_PFA_SA 243
+#endif
+typedef PfaNat<43, 15, 14, 2, SLICQ_PFA_SB, SLICQ_PFA_SA> Pfa9030;
 
 // pass A sources / destinations (Dftp<>::run / store)
 template <class PF> struct ColNat {        // column m in natural order: element i1 at 43 m + 210 i1 (mod N)
