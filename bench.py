@@ -247,6 +247,59 @@ def slice_sharding_run(nsg, dev, rank, world, steps: int, warmup: int):
     return out
 
 
+def bench_sweep(args, nsg, dev, rank, world, distributed):
+    """BASELINE.json configs[4]: throughput sweep over `--tracks` synthetic 3-min stereo tracks, dealt round-robin to the
+    ranks (sharding.shard_tracks, no data-path communication).  Every track is generated ON THE DEVICE from its own seed,
+    analysed (2 rows x 881 slices) and resynthesised for 4 targets (mask * mixture fused into the synthesis); wall clock
+    between two barriers, all tracks."""
+    import torch
+    import torch.distributed as dist
+    from xumx_slicq_b200.sharding import shard_tracks
+    Ttrack = 180 * FS
+    mine = shard_tracks(args.tracks, rank, world)
+    ctx, ctxi = {}, {}
+    gen = torch.Generator(device=dev)
+    x = torch.empty(2, Ttrack, device=dev)
+    C = nsg.forward_rows_into(ctx, x)
+    masks = [torch.stack([torch.full(tuple(c.shape), g, dtype=torch.float32, device=dev) for g in GAINS]) for c in C]
+    worst = 0.0
+
+    def one(track_id, check=False):
+        gen.manual_seed(track_id)
+        x.uniform_(-1.0, 1.0, generator=gen)
+        Cc = nsg.forward_rows_into(ctx, x)
+        y = nsg.backward_rows_masked(Cc, masks, Ttrack, ctx=ctxi)
+        return float((y[:2] - GAINS[0] * x).abs().max()) if check else 0.0
+    for t in mine[:2]:
+        worst = max(worst, one(t, check=True))
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for t in mine:
+        one(t)
+    torch.cuda.synchronize(dev)
+    if distributed:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    if rank == 0:
+        emit(({
+            "metric": "sliCQT fwd+inv audio-sec/sec", "value": args.tracks * 180.0 / wall, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.tracks, "warmup": 2, "ms_per_step": wall / max(1, len(mine)) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[4]: {args.tracks} synthetic 3-min 44.1 kHz stereo tracks (generated on the device per "
+                                   "track seed), 1 forward + 4-target synthesis each, dealt round-robin to the GPUs",
+                       "parallelism": f"tracks x{world}", "tracks_per_gpu": len(mine)},
+            "wall_s": wall, "max_abs_err_target0": worst,
+        }))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def bench_slices(args, nsg, dev, rank, world, distributed):
     """`--mode slices`: the configs[3] line on its own (strong scaling)."""
     import torch.distributed as dist
@@ -327,9 +380,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="30 s mixtures per GPU per step (Separator.forward takes a batch)")
-    ap.add_argument("--mode", default="tracks", choices=["tracks", "slices"],
+    ap.add_argument("--mode", default="tracks", choices=["tracks", "slices", "sweep"],
                     help="tracks: every rank demixes its own batch of 30 s mixtures (weak scaling, configs[1]); "
-                         "slices: ONE 3-min stereo track sharded by slice range with NCCL halo exchange (strong, configs[3])")
+                         "slices: ONE 3-min stereo track sharded by slice range with NCCL halo exchange (strong, configs[3]); "
+                         "sweep: --tracks synthetic 3-min stereo tracks dealt round-robin to the GPUs (configs[4])")
+    ap.add_argument("--tracks", type=int, default=1024, help="--mode sweep: number of 3-min tracks")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -387,6 +442,8 @@ def main():
     nsgt, insgt = make_filterbanks(base)
     if args.mode == "slices":
         return bench_slices(args, nsg, dev, rank, world, distributed)
+    if args.mode == "sweep":
+        return bench_sweep(args, nsg, dev, rank, world, distributed)
     B = args.batch
     S = nsg.n_slices(T)
     rows_f, rows_i = 2 * B, 2 * B * N_TARGETS

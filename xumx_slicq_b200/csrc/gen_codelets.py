@@ -4,7 +4,7 @@
     python xumx_slicq_b200/csrc/gen_codelets.py            # rewrites dft_codelets.cuh
     python xumx_slicq_b200/csrc/gen_codelets.py --check    # numerically validates every codelet
 
-Two families are emitted into ``dft_codelets.cuh``:
+Two families are emitted into ``dft_codelets.cuh`` (plus ``fft_sizes.inc``, the plan per bin length M):
 
 * ``dft<N, INV>(cpx (&v)[N])``   in-place complex DFT of compile-time size N with
   natural-order output, written in PACKED complex operations (slicq_cpx.cuh: one FADD2 / FMUL2 /
@@ -16,11 +16,11 @@ Two families are emitted into ``dft_codelets.cuh``:
   symmetric direct form  X[k], X[p-k] = x0 + sum a_n cos(.) -/+ i sum b_n sin(.)
   with a_n = x[n]+x[p-n], b_n = x[n]-x[p-n]  ((p-1)^2 real FMAs, all twiddles
   immediates).
-* ``rdft_sym<P>(const float (&x)[P], float* out, int stride)``  the *real* half of
-  that symmetric form for large primes (29..73): given P reals it writes
-  out[0] = sum x, out[k] = x0 + sum a_n cos(2 pi n k / P), out[P-k] = sum b_n sin(..)
-  (k = 1..(P-1)/2).  A complex DFT-P is two of these (real and imaginary parts,
-  run by two threads) plus a combine step done by the consumer (see slicq_fft.cuh).
+* ``Dftp<P, NP, INV>``  DFT of prime length P in the same symmetric direct form, STREAMED over the inputs
+  (``src.ld(n)``, one pair (n, P-n) at a time) and split BY OUTPUTS over NP threads ("parts"): part q accumulates
+  X[k], X[P-k] for its range of k (part 0 also X[0]); the 2 * pairs + 1 packed accumulators are the only long-lived
+  registers, every twiddle is an immediate of an FFMA2.  Used for the radix-43 pass of the slice FFT (NP = 2) and the
+  bin lengths M = 4 P / 8 P with P = 29 ... 73 (NP = 2 ... 4).
 
 All constants are evaluated in float64 (mpmath-free, math.cos/sin of exact
 rational angles reduced to the first octant) and rounded once to fp32.
@@ -505,9 +505,6 @@ template <int N, bool INV> SLICQ_DEVFN void dft(float2 (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = cpx_to(c[i]);
 }
-// rdft_sym<P>(x, out, stride): real symmetric half-transform for odd prime P:
-//   out[0] = sum_n x[n];  out[k*stride] = x0 + sum a_n cos(2 pi nk/P);  out[(P-k)*stride] = sum b_n sin(2 pi nk/P)
-template <int P> SLICQ_DEVFN void rdft_sym(const float (&x)[P], float* out, int stride);
 
 // Dftp<P, NP, INV>: DFT of prime length P streamed from `SRC::ld(n)` and split BY OUTPUTS over NP threads
 // ("parts"; part q accumulates the outputs k and P-k of its pair range, part 0 also k = 0):
@@ -547,7 +544,7 @@ def choose_split(M: int):
     """FFT plan for one coefficient length M (multiple of 4).
     kind 1: one thread does the whole DFT-M in registers.
     kind 2: two passes A x B through shared memory (Cooley-Tukey, table twiddles), A >= B.
-    kind 3: M = P * R with a prime P >= 29: rdft_sym<P> real/imag split + DFT-R."""
+    kind 3: M = P * R with a prime P >= 29: Dftp<P, NP> (streamed, split by outputs) + DFT-R."""
     fac = factorize(M)
     big = [p for p in fac if p >= 29]
     if big:
