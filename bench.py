@@ -549,14 +549,21 @@ def main():
     alg_step = B_UNIT * (units_f + units_i)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     achieved = alg_step / (ms_per_step * 1e-3) / 1e9
-    # DRAM bytes per (row, slice) unit from the committed ncu --set full capture (profiles/r1_ncu_summary.txt,
-    # dram__bytes_read.sum + dram__bytes_write.sum, batch 2): analysis 50.2 + 214.2 KB, synthesis 302.8 + 216.8 KB
-    traffic_step = int((50.2e3 + 214.2e3) * units_f + (302.8e3 + 216.8e3) * units_i)
+    # DRAM bytes per (row, slice) unit measured by ncu for this build (dram__bytes_read.sum + dram__bytes_write.sum of every
+    # launch of one step: profiles/r2_launches.csv -> profiles/r2_dram_traffic.json, regenerated with tools/r2_capture.sh)
+    traffic_step, traffic_src = None, "profiles/r2_dram_traffic.json not found"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
+            tr = json.load(f)
+        traffic_step = int(tr["analysis_dram_bytes_per_unit"] * units_f + tr["synthesis_dram_bytes_per_unit"] * units_i)
+        traffic_src = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic_step,
-        "traffic_note": "per step, scaled per unit from the ncu capture in profiles/ (scratch spectra round-trip "
-                        "through HBM at the default chunk size: 2.8x the algorithmic bytes on the synthesis side)",
+        "traffic_note": "DRAM bytes of one step, per-unit figures of the committed ncu launch list scaled to this step's units "
+                        "(the intermediate spectra H / T make a round trip through HBM at the default chunk size); " + traffic_src,
         "scope": "whole path: algorithmic bytes of one step (185 240 B per (row,slice) and direction) / "
                  "CUDA-event time of the step (all five kernels)",
         "peak_source": peak_src, "algorithmic_bytes_per_step": alg_step,
