@@ -75,12 +75,14 @@ def _worker(rank, world, port, T, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slice_sharding_over_gloo(world, tmp_path):
+@pytest.mark.parametrize("world,hops,extra", [(2, 4, 777), (3, 4, 777), (3, 2, 0)])
+def test_slice_sharding_over_gloo(world, hops, extra, tmp_path):
     from tests.emu.emu_backend import build_emu
     build_emu()
     hop = 9030
-    T = 4 * hop + 777          # 6 slices: uneven 3-way split, last hop partial
+    # 6 slices: uneven 3-way split, last hop partial; 2 hops / 3 ranks: S = 3, the last rank owns NO output samples
+    # (its slice lies past the signal end) but still has to deliver its halo
+    T = hops * hop + extra
     mp.spawn(_worker, args=(world, _free_port(), T, str(tmp_path)), nprocs=world, join=True)
     assert os.path.exists(tmp_path / "ok")
 

@@ -555,7 +555,7 @@ int fill_bins_params(const slicq_plan* p, const slicq_bucket_view* views, SlicqB
     bp.n_buckets = (int)p->buckets.size();
     double total = 0.0;
     for (const Bucket& b : p->buckets) total += b.cost;
-    const int target = p->target_jobs > 0 ? p->target_jobs : std::min(4440, std::max(1184, n_rs));
+    const int target = p->target_jobs > 0 ? p->target_jobs : std::min(4440, std::max(1184, 4 * n_rs));
     for (size_t i = 0; i < p->buckets.size(); ++i) {
         const Bucket& b = p->buckets[i];
         SlicqBucketArg& a = bp.b[i];
