@@ -52,7 +52,13 @@ struct PfaNat {
     static constexpr int N = P1 * P2 * P3, Q = P2 * P3, C3 = N / P3;
     static constexpr int SB = SB_, SA = SA_;                 // pitches of the (i1, i2, i3) layout between the passes
     static constexpr int SLOT = (Q + 31) / 32 * 32;          // pass A: threads per part (warp multiple >= Q)
-    static constexpr int SMEM_ELEMS = (P1 * SA > N + 2 ? P1 * SA : N + 2);
+    // Natural order as pass C sees it: row k = n / C3 of the natural index n starts at k * PN.  Lane t of pass C touches
+    // t + PN * ((c - t) mod P3): with PN a multiple of 16 words the bank depends on t alone (conflict free); with the
+    // plain pitch C3 = 645 the lanes of a half warp fall on 4 banks.
+    static constexpr int PN = (C3 + 15) / 16 * 16;
+    SLICQ_DEVFN static int natp(int n) { return n + (PN - C3) * (n / C3); }
+    static constexpr int SMEM_A_ = (P1 * SA > N + 2 ? P1 * SA : N + 2);
+    static constexpr int SMEM_ELEMS = (SMEM_A_ > P3 * PN ? SMEM_A_ : P3 * PN);
     static constexpr int I2 = cmodinv(P3, P2), I3 = cmodinv(P2, P3);   // m -> (i2, i3) = (I2 m mod P2, I3 m mod P3)
     static_assert(C3 % P3 == 1, "orbit rotation of the last axis assumes (N / P3) mod P3 == 1");
     static_assert(SA >= P2 * SB && SB >= P3, "pitches too small");
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * NT;
-                if (e < N) Z[e] = (e >= e_lo && e < e_hi) ? make_float2(xv[u].x * wv[u].x, xv[u].y * wv[u].y) : make_float2(0.f, 0.f);
+                if (e < N) Z[PF::natp(e)] = (e >= e_lo && e < e_hi) ? make_float2(xv[u].x * wv[u].x, xv[u].y * wv[u].y) : make_float2(0.f, 0.f);
             }
         }
     } else {
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             float a = 0.f, b = 0.f;
             if (sx >= 0 && sx < p.T) a = __ldg(xr + sx) * wv.x;
             if (sx + 1 >= 0 && sx + 1 < p.T) b = __ldg(xr + sx + 1) * wv.y;
-            Z[e] = make_float2(a, b);
+            Z[PF::natp(e)] = make_float2(a, b);
         }
     }
     __syncthreads();
@@ -169,10 +175,10 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
             if (t < C3) {
                 const int s = t % P3;
                 const int j0 = s ? P3 - s : 0, w = P3 - j0;      // v[c] = element j0 + c (mod P3); wraps for c >= w
-                const float2* za = Z + t + j0 * C3;
-                const float2* zb = za - N;
+                const float2* za = Z + t + j0 * PF::PN;
+                const float2* zb = za - P3 * PF::PN;
 #pragma unroll
-                for (int c = 0; c < P3; ++c) v[r][c] = cpx_ld((c >= w ? zb : za) + c * C3);
+                for (int c = 0; c < P3; ++c) v[r][c] = cpx_ld((c >= w ? zb : za) + c * PF::PN);
                 dft<P3, false>(v[r]);
             }
         }
@@ -248,42 +254,42 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     const int rsl = row * p.S + k - p.rs0;
     const int tid = threadIdx.x;
     const float2* __restrict__ Trow = p.spec + (long long)rsl * p.spec_stride;
-    // ---- R[f] = plane0[f] + plane1[f], f in [0, N]: ONE memory round trip for the whole row.  Plane 0 goes
-    // straight into Z (cp.async, 16 bytes = two positions per copy; rows are 16-byte aligned), plane 1 into
-    // registers; every thread then adds its own chunks (no barrier between the copy and the add).  The overflow
-    // entry of the thread (positions covered twice inside one plane) travels in the same round.
+    // ---- R[f] = plane0[f] + plane1[f] (+ overflow), f in [0, N], and the Hermitian pre-processing, with ONE memory round
+    // trip and one pass over shared memory.  Plane 0 lands in Z by bulk copy (TMA engine: no registers, no load/store
+    // pipe traffic); meanwhile every thread loads plane 1 at ITS pairs (k, N - k) into registers.  After the copy has
+    // landed (mbarrier) and the overflow entries are added, a thread owns its pairs exclusively: it adds plane 1,
+    // pre-processes and writes back in place.
     if (!(SLICQ_DBG_SKIP & 1)) {
-    constexpr int NV = N / 2 + 1, NR = (NV + NT - 1) / NT;   // 16-byte chunks (the last holds f = N and one pad), chunks per thread
+    constexpr int NP2 = (N / 2 + NT) / NT;      // pairs (k, N-k) per thread
+    constexpr unsigned ROW_BYTES = (N / 2 + 1) * 16u;   // positions 0 .. N and one pad, rows are 16-byte aligned
+#ifdef SLICQ_EMU
+    unsigned long long bar_[1];
+#else
+    __shared__ __align__(8) unsigned long long bar_[1];
+#endif
+    if (tid == 0) mbar_init(bar_, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar_, ROW_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(Trow + p.t.pl_off);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(Z);
+        constexpr unsigned PIECE = 9040;        // a few copies in flight instead of one long one
+        for (unsigned o = 0; o < ROW_BYTES; o += PIECE)
+            bulk_g2s(dst + o, src + o, (ROW_BYTES - o < PIECE) ? ROW_BYTES - o : PIECE, bar_);
+    }
     {
-        const float4* __restrict__ q0 = reinterpret_cast<const float4*>(Trow + p.t.pl_off);
-        const float4* __restrict__ q1 = reinterpret_cast<const float4*>(Trow + p.t.pl_off + p.t.pl_len);
-        float4* Z4 = reinterpret_cast<float4*>(Z);
+        const float2* __restrict__ P1 = Trow + p.t.pl_off + p.t.pl_len;
+        float2 b0[NP2], b1[NP2];
 #pragma unroll
-        for (int u = 0; u < NR; ++u) {
-            const int i = tid + u * NT;
-            if (i < NV) cp_async16(Z4 + i, q0 + i);
-        }
-        cp_async_commit();
-        float4 b[NR];
-#pragma unroll
-        for (int u = 0; u < NR; ++u) {
-            const int i = tid + u * NT;
-            if (i < NV) b[u] = __ldg(q1 + i);
+        for (int u = 0; u < NP2; ++u) {
+            const int kk = tid + u * NT;
+            if (kk <= N / 2) { b0[u] = __ldg(P1 + kk); b1[u] = __ldg(P1 + N - kk); }
         }
         int4 xe = make_int4(-1, 0, -1, 0);
         if (tid < p.t.n_ex) xe = __ldg(p.t.ex + tid);
         float2 x2 = make_float2(0.f, 0.f), x3 = make_float2(0.f, 0.f);
         if (xe.x >= 0) { x2 = __ldg(Trow + xe.y); if (xe.z >= 0) x3 = __ldg(Trow + xe.z); }
-        cp_async_wait<0>();
-#pragma unroll
-        for (int u = 0; u < NR; ++u) {
-            const int i = tid + u * NT;
-            if (i < NV) {
-                const float4 a = Z4[i];
-                Z4[i] = make_float4(a.x + b[u].x, a.y + b[u].y, a.z + b[u].z, a.w + b[u].w);
-            }
-        }
-        __syncthreads();
+        mbar_wait(bar_, 0);
         // overflow entries: position f also receives T[off0] (+ T[off1]); entries have distinct f
         if (xe.x >= 0) { Z[xe.x].x += x2.x + x3.x; Z[xe.x].y += x2.y + x3.y; }
         for (int i = tid + NT; i < p.t.n_ex; i += NT) {
@@ -298,7 +304,6 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             // only in time: order them after the overflow pass
             __syncthreads();
             const float2* __restrict__ P0 = Trow + p.t.pl_off;
-            const float2* __restrict__ P1 = P0 + p.t.pl_len;
             for (int f = 1 + tid; f <= p.t.pad_l; f += NT) {
                 const float2 a = __ldg(P0 - f), b = __ldg(P1 - f);
                 Z[f].x += a.x + b.x; Z[f].y -= a.y + b.y;
@@ -308,23 +313,15 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
                 Z[N - f].x += a.x + b.x; Z[N - f].y -= a.y + b.y;
             }
         }
-    }
-    // ---- Hermitian pre-processing, in place: Z[k] = E + i conj(w^k) O, Z[N-k] = conj(E - i conj(w^k) O)
-    {
-        constexpr int NP2 = (N / 2 + NT) / NT;      // pairs (k, N-k) per thread
-        float2 wk[NP2];
-#pragma unroll
-        for (int u = 0; u < NP2; ++u) {
-            const int kk = tid + u * NT;
-            if (kk <= N / 2) wk[u] = __ldg(p.t.post_tw + kk);
-        }
         __syncthreads();
+        // ---- plane sum + Hermitian pre-processing, in place: Z[k] = E + i conj(w^k) O, Z[N-k] = conj(E - i conj(w^k) O)
 #pragma unroll
         for (int u = 0; u < NP2; ++u) {
             const int kk = tid + u * NT;
             if (kk > N / 2) continue;
-            const cpx rk = cpx_ld(Z + kk);
-            const cpx rn = cpx_ld(Z + N - kk);
+            const float2 wk = __ldg(p.t.post_tw + kk);
+            const cpx rk = cadd(cpx_ld(Z + kk), cpx_from(b0[u]));
+            const cpx rn = cadd(cpx_ld(Z + N - kk), cpx_from(b1[u]));
             if (kk == 0) {
                 // imaginary parts of DC / Nyquist are ignored by a C2R transform (nsigtf.py:103)
                 const float es = (p.t.adjoint & 2) ? 2.f : 1.f;     // adjoint of the analysis: DC / Nyquist count twice
@@ -333,7 +330,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             } else {
                 const cpx E = caddc(rk, rn);                 // rk + conj(rn)
                 const cpx O = csubc(rk, rn);                 // rk - conj(rn)
-                const cpx t = cmulwc(O, wk[u]);              // conj(w^k) O
+                const cpx t = cmulwc(O, wk);                 // conj(w^k) O
                 cpx_st(Z + kk, caddi(E, t));                 // E + i t
                 cpx_st(Z + N - kk, cconjp(csubi(E, t)));     // conj(E - i t)
             }
@@ -366,10 +363,10 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             if (t < C3) {
                 const int s = t % P3;
                 const int j0 = s ? P3 - s : 0, w = P3 - j0;
-                float2* za = Z + t + j0 * C3;
-                float2* zb = za - N;
+                float2* za = Z + t + j0 * PF::PN;
+                float2* zb = za - P3 * PF::PN;
 #pragma unroll
-                for (int c = 0; c < P3; ++c) cpx_st((c >= w ? zb : za) + c * C3, v[r][c]);
+                for (int c = 0; c < P3; ++c) cpx_st((c >= w ? zb : za) + c * PF::PN, v[r][c]);
             }
         }
     }
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     if (p.t.adjoint & 2) {
         // adjoint of the analysis: the slicing window multiplies the slice before the overlap-add
         const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
-        for (int n = tid; n < N; n += NT) { const float2 w = __ldg(tw2 + n); Z[n].x *= w.x; Z[n].y *= w.y; }
+        for (int n = tid; n < N; n += NT) { const float2 w = __ldg(tw2 + n); float2& z = Z[PF::natp(n)]; z.x *= w.x; z.y *= w.y; }
         // every thread reads back exactly the elements it scaled (same n = tid + i NT below): no barrier
     }
     if (vec && add1 == add2) {
@@ -397,7 +394,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
         for (int n0 = tid; n0 < N; n0 += U * NT) {
             cpx z[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (n0 + u * NT < N) z[u] = cpx_ld(Z + n0 + u * NT);
+            for (int u = 0; u < U; ++u) if (n0 + u * NT < N) z[u] = cpx_ld(Z + PF::natp(n0 + u * NT));
             if (add1) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) if (n0 + u * NT < N) slicq_red_add2(reinterpret_cast<float*>(y2 + n0 + u * NT), cpx_to(z[u]));
@@ -408,7 +405,7 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
         }
     } else {
         for (int n = tid; n < N; n += NT) {
-            const float2 z = Z[n];
+            const float2 z = Z[PF::natp(n)];
             const bool first = n < N / 2;
             const bool add = first ? add1 : add2;
             if (first && first_to_halo) {

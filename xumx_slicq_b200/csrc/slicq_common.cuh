@@ -112,6 +112,40 @@ SLICQ_DEVFN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "
 template <int N> SLICQ_DEVFN void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+// ---------------------------------------------------------------------------------------
+// bulk asynchronous global -> shared copy (cp.async.bulk, the TMA engine's linear mode) completing on an mbarrier: the
+// bytes land in shared memory without passing through the load/store pipe of the SM at all.  dst / src 16-byte aligned,
+// bytes a multiple of 16.  One thread arms the barrier and issues the copies; every thread that reads the data waits.
+#ifdef SLICQ_EMU
+static inline void mbar_init(unsigned long long*, int) {}
+static inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+static inline void bulk_g2s(void* d, const void* s, unsigned bytes, unsigned long long*) { memcpy(d, s, bytes); }
+static inline void mbar_wait(unsigned long long*, unsigned) { slicq_emu_sync(); }   // all threads of the CTA call it
+#else
+SLICQ_DEVFN void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SLICQ_DEVFN void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+SLICQ_DEVFN void bulk_g2s(void* d, const void* s, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+SLICQ_DEVFN void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+#endif
+
 #define SLICQ_MAX_BUCKETS 96
 #define SLICQ_MAX_M 292
 
