@@ -56,6 +56,10 @@ __device__ long long* g_bins_phase_buf = nullptr;   // this header is included b
 #define SLICQ_CUNIT(u) (u)
 #endif
 
+// independent 16-byte loads in flight per thread in the input loop of the single-thread synthesis transforms
+#ifndef SLICQ_UK1
+#define SLICQ_UK1 4
+#endif
 struct JobCtx {
     int u0, u1;     // unit range of this job (indices local to the chunk)
     int F;          // bins in the bucket
@@ -180,11 +184,28 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
         fill_slot_off(so, b, j, base, ng);
         __syncthreads();
         if (vec) {
-            for (int t = tid; t < ng * j.F * (M / 2); t += blockDim.x) {
-                const int slot = t / (M / 2), n = 2 * (t - slot * (M / 2));
-                const float4 v = *reinterpret_cast<const float4*>(b.ptr + so[slot] + n);
-                sm[slot * PITCH + n] = make_float2(v.x, v.y);
-                sm[slot * PITCH + n + 1] = make_float2(v.z, v.w);
+            // four independent 16-byte loads in flight per thread (a rolled loop would wait for each in turn)
+            constexpr int U = SLICQ_UK1;
+            const int tot = ng * j.F * (M / 2);
+            for (int t0 = tid; t0 < tot; t0 += U * blockDim.x) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int t = t0 + u * blockDim.x;
+                    if (t < tot) {
+                        const int slot = t / (M / 2), n = 2 * (t - slot * (M / 2));
+                        v[u] = *reinterpret_cast<const float4*>(b.ptr + so[slot] + n);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int t = t0 + u * blockDim.x;
+                    if (t < tot) {
+                        const int slot = t / (M / 2), n = 2 * (t - slot * (M / 2));
+                        sm[slot * PITCH + n] = make_float2(v[u].x, v[u].y);
+                        sm[slot * PITCH + n + 1] = make_float2(v[u].z, v[u].w);
+                    }
+                }
             }
         } else if (b.mptr == nullptr) {
             for (int t = tid; t < ng * j.F * M; t += blockDim.x) {
