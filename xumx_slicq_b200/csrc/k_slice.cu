@@ -342,7 +342,16 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     if (!(SLICQ_DBG_SKIP & 4)) pass_b<PF, true>(Z);
     // ---- pass C (last): thread t owns the orbit {t + C3 j} of the OUTPUT; element j has i3 = (t + j) mod P3.  The
     // outputs go back to Z in natural order (all tasks of a thread stay in registers until every thread has read its
-    // inputs), and leave with coalesced stores / reductions.
+    // inputs) and leave as 14 bulk copies / bulk reductions (one per row of C3 = 645 sample pairs, issued by lane 0 of
+    // warp j; TMA engine: no registers, no load/store pipe traffic) plus one ordinary access per row for the element that
+    // the 16-byte alignment rule leaves over.  Row j of the staging area starts at Z + PN j + sh_j with sh_j in {0, 1}
+    // chosen so that the 16-byte aligned part of the row in y is 16-byte aligned in shared memory as well (a row is
+    // 5160 bytes: the alignment of its start in y alternates from row to row).
+    // slice sample pair n = (2n, 2n+1) goes to y index tb + 2n;  first half (n < N/2) = hop k-1, second half = hop k
+    static_assert(P3 % 2 == 0 && (P3 / 2) * C3 == N / 2 && NT / 32 >= P3, "row structure of the output staging");
+    const long long tb = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;
+    float* __restrict__ yr = p.x + row * p.x_row_stride;
+    const int q0 = (int)((reinterpret_cast<uintptr_t>(yr + tb) >> 3) & 1);       // 1: y + tb is 8 but not 16 bytes aligned
     {
         constexpr int NRC = (C3 + NT - 1) / NT;
         cpx v[NRC][P3];
@@ -363,17 +372,17 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             if (t < C3) {
                 const int s = t % P3;
                 const int j0 = s ? P3 - s : 0, w = P3 - j0;
-                float2* za = Z + t + j0 * PF::PN;
-                float2* zb = za - P3 * PF::PN;
+                const int qq = (q0 + j0) & 1;                 // sh of the row of element c: qq for even c, 1 - qq for odd c
+                float2* za0 = Z + t + j0 * PF::PN + qq;
+                float2* za1 = Z + t + j0 * PF::PN + 1 - qq;
+                float2* zb0 = za0 - P3 * PF::PN;
+                float2* zb1 = za1 - P3 * PF::PN;
 #pragma unroll
-                for (int c = 0; c < P3; ++c) cpx_st((c >= w ? zb : za) + c * PF::PN, v[r][c]);
+                for (int c = 0; c < P3; ++c) cpx_st((c >= w ? ((c & 1) ? zb1 : zb0) : ((c & 1) ? za1 : za0)) + c * PF::PN, v[r][c]);
             }
         }
     }
-    __syncthreads();
-    // slice sample pair n = (2n, 2n+1) goes to y index tb + 2n;  first half (n < N/2) = hop k-1, second half = hop k
-    const long long tb = (p.k0 + k - 1) * (long long)p.t.hop - p.t0;
-    float* __restrict__ yr = p.x + row * p.x_row_stride;
+    auto stage = [&](int n) { const int j = n / C3; return n + (PF::PN - C3) * j + ((q0 + j) & 1); };   // natural index -> staging slot
     const bool accumulate = p.parity != 0;
     // the last slice of the call has no right neighbour: its second half is stored even when odd
     const bool second_store = !accumulate || (k + 1 >= p.S);
@@ -384,28 +393,32 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
     if (SLICQ_DBG_SKIP & 8) return;
     if (p.t.adjoint & 2) {
         // adjoint of the analysis: the slicing window multiplies the slice before the overlap-add
+        __syncthreads();
         const float2* __restrict__ tw2 = reinterpret_cast<const float2*>(p.t.tukey);
-        for (int n = tid; n < N; n += NT) { const float2 w = __ldg(tw2 + n); float2& z = Z[PF::natp(n)]; z.x *= w.x; z.y *= w.y; }
-        // every thread reads back exactly the elements it scaled (same n = tid + i NT below): no barrier
+        for (int n = tid; n < N; n += NT) { const float2 w = __ldg(tw2 + n); float2& z = Z[stage(n)]; z.x *= w.x; z.y *= w.y; }
     }
-    if (vec && add1 == add2) {
-        float2* __restrict__ y2 = reinterpret_cast<float2*>(yr + tb);
-        constexpr int U = 7;
-        for (int n0 = tid; n0 < N; n0 += U * NT) {
-            cpx z[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) if (n0 + u * NT < N) z[u] = cpx_ld(Z + PF::natp(n0 + u * NT));
-            if (add1) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (n0 + u * NT < N) slicq_red_add2(reinterpret_cast<float*>(y2 + n0 + u * NT), cpx_to(z[u]));
+    fence_proxy_async();
+    __syncthreads();
+    if (vec) {
+        const int j = tid >> 5, lane = tid & 31;
+        if (j < P3 && lane < 2) {
+            const int sh = (q0 + j) & 1;
+            const bool add = (j < P3 / 2) ? add1 : add2;
+            float2* __restrict__ y2 = reinterpret_cast<float2*>(yr + tb) + C3 * j;
+            float2* zr = Z + PF::PN * j + sh;                        // element e of the row at zr[e]
+            if (lane == 0) {
+                // elements sh .. sh + C3 - 2: 16-byte aligned on both sides
+                if (add) bulk_s2g_add_f32(y2 + sh, zr + sh, (C3 - 1) * 8u); else bulk_s2g(y2 + sh, zr + sh, (C3 - 1) * 8u);
+                bulk_wait_read();
             } else {
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (n0 + u * NT < N) cpx_st(y2 + n0 + u * NT, z[u]);
+                const int e = sh ? 0 : C3 - 1;
+                const float2 z = zr[e];
+                if (add) slicq_red_add2(reinterpret_cast<float*>(y2 + e), z); else y2[e] = z;
             }
         }
     } else {
         for (int n = tid; n < N; n += NT) {
-            const float2 z = Z[PF::natp(n)];
+            const float2 z = Z[stage(n)];
             const bool first = n < N / 2;
             const bool add = first ? add1 : add2;
             if (first && first_to_halo) {

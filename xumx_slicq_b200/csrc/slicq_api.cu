@@ -272,7 +272,8 @@ extern "C" int slicq_plan_create(const slicq_tables* t, slicq_plan** out) {
         const int nthr = slicq_bins_threads();
         int gt = nthr / (b.n_bins * fft_threads_per_transform(*f));
         if (gt < 1) gt = 1;
-        while (gt > 1 && b.n_bins * gt * b.smem_per_fft > 48 * 1024) --gt;
+        static const int stage_kb = getenv("SLICQ_BINS_STAGE_KB") ? atoi(getenv("SLICQ_BINS_STAGE_KB")) : 48;   // tuning aid
+        while (gt > 1 && b.n_bins * gt * b.smem_per_fft > stage_kb * 1024) --gt;
         if (b.n_bins * fft_threads_per_transform(*f) > nthr) {
             delete p;
             return fail(SLICQ_E_UNSUPPORTED, "bucket has too many bins for one CTA");

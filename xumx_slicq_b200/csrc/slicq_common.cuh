@@ -146,6 +146,32 @@ SLICQ_DEVFN void mbar_wait(unsigned long long* bar, unsigned parity) {
 }
 #endif
 
+// bulk shared -> global copy / float32 reduction (TMA engine, linear mode): the data leaves shared memory without passing
+// through registers or the load/store pipe.  Both addresses 16-byte aligned, bytes a multiple of 16.  Shared memory written
+// with ordinary stores must be made visible to the async proxy first (fence_proxy_async by the writers, then a barrier);
+// the issuing thread keeps the source alive until bulk_wait_read() returns.
+#ifdef SLICQ_EMU
+static inline void fence_proxy_async() {}
+static inline void bulk_s2g(void* g, const void* s, unsigned bytes) { memcpy(g, s, bytes); }
+static inline void bulk_s2g_add_f32(void* g, const void* s, unsigned bytes) {
+    float* d = static_cast<float*>(g); const float* q = static_cast<const float*>(s);
+    for (unsigned i = 0; i < bytes / 4; ++i) d[i] += q[i];
+}
+static inline void bulk_wait_read() {}
+#else
+SLICQ_DEVFN void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+SLICQ_DEVFN void bulk_s2g(void* g, const void* s, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(s)), "r"(bytes) : "memory");
+}
+SLICQ_DEVFN void bulk_s2g_add_f32(void* g, const void* s, unsigned bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(s)), "r"(bytes) : "memory");
+}
+SLICQ_DEVFN void bulk_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
 #define SLICQ_MAX_BUCKETS 96
 #define SLICQ_MAX_M 292
 
