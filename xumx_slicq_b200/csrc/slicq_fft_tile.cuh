@@ -60,6 +60,13 @@ __device__ long long* g_bins_phase_buf = nullptr;   // this header is included b
 #ifndef SLICQ_UK1
 #define SLICQ_UK1 4
 #endif
+// two-pass synthesis transforms with A + B up to this bound prefetch their next inputs into registers (see syn_two_pass)
+#ifndef SLICQ_K3_PAD
+#define SLICQ_K3_PAD 0
+#endif
+#ifndef SLICQ_PIPE_MAX
+#define SLICQ_PIPE_MAX 26
+#endif
 struct JobCtx {
     int u0, u1;     // unit range of this job (indices local to the chunk)
     int F;          // bins in the bucket
@@ -360,20 +367,34 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
     const float2* twp = twsm + n2;
     __syncthreads();
     BINS_DECL;
-    for (int base = j.u0; base < j.u1; base += j.gt) {
-        BINS_T(t0_);
-        BINS_T0(tl_);
+    // Software pipeline (sizes whose two register sets fit, A + B <= SLICQ_PIPE_MAX): the inputs of the NEXT group of units are
+    // requested right after pass 1 has put its outputs into shared memory, so that they travel during the barrier and pass 2.
+    constexpr bool PIPE = (A + B <= SLICQ_PIPE_MAX);
+    float2 v[A];
+    int rowk[2] = {0, 0};           // (row, slice) of the unit whose inputs sit in v
+    auto request = [&](int base) {
         const int g = base + gs1;
         if (act1 && g < j.u1) {
             const int rs = SLICQ_CUNIT(j.rs0 + g);
             const int row = rs / j.S, k = rs - row * j.S;
             const int rowx = j.x_rows ? row % j.x_rows : row;
             const float2* src = b.ptr + rowx * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
-            float2 v[A];
 #pragma unroll
-            for (int n1 = 0; n1 < A; ++n1) v[n1] = cneg_if(src[B * n1], odd != (((B * n1) & 1) != 0));  // (-1)^(B n1 + n2)
+            for (int n1 = 0; n1 < A; ++n1) v[n1] = src[B * n1];
+            rowk[0] = row; rowk[1] = k;
+        }
+    };
+    if (PIPE) request(j.u0);
+    for (int base = j.u0; base < j.u1; base += j.gt) {
+        BINS_T(t0_);
+        BINS_T0(tl_);
+        const int g = base + gs1;
+        if (!PIPE) request(base);
+        if (act1 && g < j.u1) {
+#pragma unroll
+            for (int n1 = 0; n1 < A; ++n1) v[n1] = cneg_if(v[n1], odd != (((B * n1) & 1) != 0));  // (-1)^(B n1 + n2)
             if (b.mptr != nullptr) {
-                const float* msrc = b.mptr + row * b.ms_row + f1 * b.ms_bin + k * b.ms_slice + n2;
+                const float* msrc = b.mptr + rowk[0] * b.ms_row + f1 * b.ms_bin + rowk[1] * b.ms_slice + n2;
 #pragma unroll
                 for (int n1 = 0; n1 < A; ++n1) v[n1] = cscale(v[n1], msrc[B * n1]);
             }
@@ -383,6 +404,7 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
 #pragma unroll
             for (int k1 = 1; k1 < A; ++k1) y1[k1 * BP] = cmul(v[k1], twp[k1 * B]);
         }
+        if (PIPE && base + j.gt < j.u1) request(base + j.gt);
         BINS_T(t1_);
         __syncthreads();
         BINS_T(t2_);
@@ -522,6 +544,9 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
     long long* so = reinterpret_cast<long long*>(smf);
     float2* sm = reinterpret_cast<float2*>(smf + SLICQ_SLOT_BYTES / sizeof(float));
     // job twiddles [k1][n2] = exp(-2 pi i n2 k1 / M) (-1)^n2, the bucket's dual windows and the T-row offsets of its bins
+    // slot pitch M: pass 2 then reads column k1 of slot s at (s R + k1) P + n -- a single odd stride across the lanes
+    // (a pitch of M + P put every half warp on 8 bank pairs: 2-way conflicts on the NP-times repeated loads of pass 2)
+    constexpr int SP = M + SLICQ_K3_PAD * P;
     float2* twsm = sm + (size_t)j.gt * j.F * (M + P);
     float* wsm = reinterpret_cast<float*>(twsm + M);
     const int coff_first = __ldg(p.t.bin_coff + j.first_bin);
@@ -559,7 +584,7 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
                 for (int n1 = 0; n1 < R; ++n1) v[n1] = cmulr(v[n1], msrc[P * n1]);
             }
             dft<R, false>(v);
-            float2* o = sm + s * (M + P) + c2;
+            float2* o = sm + s * SP + c2;
             const float2* twp = twsm + c2;
 #pragma unroll
             for (int k1 = 0; k1 < R; ++k1) cpx_st(o + k1 * P, cmulw(v[(k1 + R / 2) % R], twp[k1 * P]));
@@ -572,7 +597,7 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             if (c >= ncol) continue;
             const int s = c / R, k1 = c - s * R;
             const int gs = s / j.F, f = s - gs * j.F;
-            PrimeSrcSyn<M> src; src.p = sm + s * (M + P) + k1 * P;
+            PrimeSrcSyn<M> src; src.p = sm + s * SP + k1 * P;
             cpx o[D::NOUT];
             D::run(part, src, o);
             PrimeDstSyn dst;
