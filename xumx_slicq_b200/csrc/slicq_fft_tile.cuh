@@ -61,6 +61,11 @@ __device__ long long* g_bins_phase_buf = nullptr;   // this header is included b
 #define SLICQ_UK1 4
 #endif
 // two-pass synthesis transforms with A + B up to this bound prefetch their next inputs into registers (see syn_two_pass)
+// tuning experiments only (results invalid): bit 0 no coefficient loads, bit 1 no first-pass transform, bit 2 no second-pass
+// transform, bit 3 no stores to the plane rows (synthesis kernels)
+#ifndef SLICQ_DBG_BINS
+#define SLICQ_DBG_BINS 0
+#endif
 #ifndef SLICQ_K3_PAD
 #define SLICQ_K3_PAD 0
 #endif
@@ -201,7 +206,7 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
                     const int t = t0 + u * blockDim.x;
                     if (t < tot) {
                         const int slot = t / (M / 2), n = 2 * (t - slot * (M / 2));
-                        v[u] = *reinterpret_cast<const float4*>(b.ptr + so[slot] + n);
+                        v[u] = (SLICQ_DBG_BINS & 1) ? make_float4(1.f, 2.f, (float)n, 0.f) : *reinterpret_cast<const float4*>(b.ptr + so[slot] + n);
                     }
                 }
 #pragma unroll
@@ -230,7 +235,7 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
             float2 v[M];
 #pragma unroll
             for (int n = 0; n < M; ++n) v[n] = cneg_if(stage[n], n & 1);
-            dft<M, false>(v);
+            if (!(SLICQ_DBG_BINS & 6)) dft<M, false>(v);
 #pragma unroll
             for (int m = 0; m < M; ++m) stage[m] = v[m];
         }
@@ -242,6 +247,7 @@ SLICQ_DEVFN void syn_single(const SlicqBinsParams& p, const SlicqBucketArg& b, c
             const float2* src = sm + (g * j.F + fb) * PITCH + n;
             const float w0 = wsm[e], w1 = wsm[e + 1];
             const int off = (n < tob[3 * fb + 1] ? tob[3 * fb + 2] : tob[3 * fb]) + n;
+            if ((SLICQ_DBG_BINS & 8) && p.n_rs >= 0) continue;
             *reinterpret_cast<float4*>(p.spec + SLICQ_TROW(base + g) * p.spec_stride + off) =
                 make_float4(src[0].x * w0, src[0].y * w0, src[1].x * w1, src[1].y * w1);
         }
@@ -380,7 +386,7 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             const int rowx = j.x_rows ? row % j.x_rows : row;
             const float2* src = b.ptr + rowx * b.s_row + f1 * b.s_bin + k * b.s_slice + n2;
 #pragma unroll
-            for (int n1 = 0; n1 < A; ++n1) v[n1] = src[B * n1];
+            for (int n1 = 0; n1 < A; ++n1) v[n1] = (SLICQ_DBG_BINS & 1) ? make_float2((float)n1, (float)k) : src[B * n1];
             rowk[0] = row; rowk[1] = k;
         }
     };
@@ -399,7 +405,7 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
                 for (int n1 = 0; n1 < A; ++n1) v[n1] = cscale(v[n1], msrc[B * n1]);
             }
             BINS_SET(tl_);
-            dft<A, false>(v);
+            if (!(SLICQ_DBG_BINS & 2)) dft<A, false>(v);
             y1[0] = v[0];
 #pragma unroll
             for (int k1 = 1; k1 < A; ++k1) y1[k1 * BP] = cmul(v[k1], twp[k1 * B]);
@@ -416,7 +422,8 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             float2 v[B];
 #pragma unroll
             for (int n = 0; n < B; ++n) v[n] = src[n];
-            dft<B, false>(v);
+            if (!(SLICQ_DBG_BINS & 4)) dft<B, false>(v);
+            if ((SLICQ_DBG_BINS & 8) && p.n_rs >= 0) continue;
             float2* row = p.spec + SLICQ_TROW(base + (c.x & 0xffff)) * p.spec_stride;
             float2* o = row + c.y + k1;
             const float* wp = wsm + (c.x >> 16) * M + k1;
@@ -577,13 +584,13 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             const float2* src = b.ptr + so[s] + c2;
             cpx v[R];
 #pragma unroll
-            for (int n1 = 0; n1 < R; ++n1) v[n1] = cpx_ld(src + P * n1);
+            for (int n1 = 0; n1 < R; ++n1) v[n1] = (SLICQ_DBG_BINS & 1) ? cpx_make((float)n1, (float)c2) : cpx_ld(src + P * n1);
             if (b.mptr != nullptr) {
                 const float* msrc = b.mptr + so[256 + s] + c2;
 #pragma unroll
                 for (int n1 = 0; n1 < R; ++n1) v[n1] = cmulr(v[n1], msrc[P * n1]);
             }
-            dft<R, false>(v);
+            if (!(SLICQ_DBG_BINS & 2)) dft<R, false>(v);
             float2* o = sm + s * SP + c2;
             const float2* twp = twsm + c2;
 #pragma unroll
@@ -599,7 +606,9 @@ SLICQ_DEVFN void syn_prime(const SlicqBinsParams& p, const SlicqBucketArg& b, co
             const int gs = s / j.F, f = s - gs * j.F;
             PrimeSrcSyn<M> src; src.p = sm + s * SP + k1 * P;
             cpx o[D::NOUT];
-            D::run(part, src, o);
+            if (!(SLICQ_DBG_BINS & 4)) D::run(part, src, o);
+            else { for (int q = 0; q < D::NOUT; ++q) o[q] = src.ld(q); }
+            if ((SLICQ_DBG_BINS & 8) && p.n_rs >= 0) continue;
             PrimeDstSyn dst;
             dst.o = p.spec + SLICQ_TROW(base + gs) * p.spec_stride + tob[3 * f] + k1;
             dst.w = wsm + f * M + k1; dst.R = R;
