@@ -427,6 +427,13 @@ SLICQ_DEVFN void syn_two_pass(const SlicqBinsParams& p, const SlicqBucketArg& b,
             float2* row = p.spec + SLICQ_TROW(base + (c.x & 0xffff)) * p.spec_stride;
             float2* o = row + c.y + k1;
             const float* wp = wsm + (c.x >> 16) * M + k1;
+            if (SLICQ_DBG_BINS & 16) {   // probe: the same bytes as fully coalesced stores (garbage layout)
+                float2* oc = p.spec + SLICQ_TROW(base) * p.spec_stride + t;
+                const int nt = ng * j.F * A;
+#pragma unroll
+                for (int k2 = 0; k2 < B; ++k2) oc[k2 * nt] = make_float2(v[k2].x * wp[A * k2], v[k2].y * wp[A * k2]);
+                continue;
+            }
             // overflow counts never exceed A (checked by slicq_plan_create): only output k2 = 0 can be diverted
             {
                 const float w = wp[0];
