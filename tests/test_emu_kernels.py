@@ -155,6 +155,18 @@ def test_slice_range_sharding_is_bitwise(base):
     assert torch.equal(y, y_full)
 
 
+def test_output_alignment_paths_are_bitwise(base):
+    """The same samples through the bulk-copy path (8-byte aligned rows, both 16-byte phases) and the sample-by-sample
+    path (odd row stride) of the synthesis slice kernel: lengths T, T-1, T-2 change the row stride of y only."""
+    nsg = base.nsgt
+    T = 3 * 9030
+    x = torch.from_numpy(np.random.RandomState(11).uniform(-1, 1, (3, T)).astype(np.float32))
+    C = nsg.forward_rows(x)
+    y = nsg.backward_rows(C, T)
+    for cut in (1, 2):
+        assert torch.equal(nsg.backward_rows(C, T - cut), y[:, :T - cut]), cut
+
+
 def test_errors(base, emu):
     from xumx_slicq_b200 import make_filterbanks
     with pytest.raises(ValueError):

@@ -205,6 +205,22 @@ def test_chunking_is_invisible(dev):
         assert torch.equal(y, outs[0][1])
 
 
+def test_output_alignment_paths_bitwise(base, dev):
+    """The synthesis writes a slice as bulk copies / bulk reductions when its place in y is 8-byte aligned (16-byte
+    aligned part by the TMA engine, one leftover element per row) and sample by sample otherwise.  The row stride of y
+    is the requested length: lengths T, T-1, T-2, T-3 put the rows of a batch on every alignment, and every sample is
+    the same two-term sum in all of them."""
+    nsg = base.nsgt
+    T = 12 * 9030
+    x = torch.rand(5, T, device=dev) * 2 - 1
+    C = nsg.forward_rows(x)
+    y = nsg.backward_rows(C, T)
+    for cut in (1, 2, 3):
+        yc = nsg.backward_rows(C, T - cut)
+        assert yc.shape == (5, T - cut)
+        assert torch.equal(yc, y[:, :T - cut]), cut
+
+
 def test_slice_range_sharding_bitwise(base, dev):
     """BASELINE.json configs[3] on one GPU with virtual ranks: slices split into contiguous ranges,
     one half-slice halo per boundary, result bitwise equal to the unsharded transform."""
