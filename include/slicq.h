@@ -96,7 +96,8 @@ int64_t slicq_plan_num_slices(const slicq_plan* plan, int64_t n_samples);
 /* Scratch (device) bytes needed by a forward / inverse call over n_rows x n_slices units.
  * Scratch holds the intermediate spectra of one chunk of units (analysis: padded half spectra, 73.6 KB per unit;
  * synthesis: two planes of windowed bin spectra, 147 KB per unit); SLICQ_CHUNK_MB bounds a chunk (default 2 GiB:
- * one chunk per call -- measured faster than L2-sized chunks). */
+ * one chunk per call -- measured faster than L2-sized chunks).  The scratch pointer must be 16-byte
+ * aligned (its rows are moved with 16-byte vector and bulk copies); a misaligned one is refused with SLICQ_E_SCRATCH. */
 size_t slicq_scratch_bytes(const slicq_plan* plan, int64_t n_rows, int64_t n_slices, int inverse);
 
 /* Analysis.  x: [n_rows] rows of float32, row r at x + r*x_row_stride, n_samples valid samples

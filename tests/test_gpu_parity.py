@@ -254,6 +254,17 @@ def test_error_paths(base, dev):
         base.nsgt.backward_rows([torch.zeros(1, 1, 2, 16, dtype=torch.complex64, device=dev)], 100)
     with pytest.raises(ValueError):      # bin lengths beyond the compiled per-bin transforms (M up to 1664 here)
         NSGTBase("cqlog", 48, 100.0, device=dev).nsgt.plan()
+    # C-ABI: a scratch pointer that is not 16-byte aligned is refused (its rows move as 16-byte vector / bulk copies)
+    from xumx_slicq_b200 import _cabi
+    plan = base.nsgt.plan(dev)
+    x = torch.zeros(1, 9030, device=dev)
+    S = base.nsgt.n_slices(9030)
+    nbytes = plan.scratch_bytes(1, S, False)
+    scratch = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
+    coefs = torch.empty(S * base.nsgt.tables.sum_M, dtype=torch.complex64, device=dev)
+    with pytest.raises(_cabi.SlicqError):
+        plan.forward_packed(x.data_ptr(), 1, x.stride(0), 9030, 0, 0, S, coefs.data_ptr(), scratch.data_ptr() + 8, nbytes,
+                            torch.cuda.current_stream(dev).cuda_stream)
 
 
 def test_transform_stream_matches_direct_calls(base, dev):

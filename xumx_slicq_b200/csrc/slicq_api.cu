@@ -625,6 +625,7 @@ int forward_impl(const slicq_plan* p, const float* x, int64_t n_rows, int64_t x_
     if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
     if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 0) || !scratch)
         return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
+    if (reinterpret_cast<uintptr_t>(scratch) & 15) return fail(SLICQ_E_SCRATCH, "scratch buffer must be 16-byte aligned");
     for (size_t i = 0; i < p->buckets.size(); ++i)
         if (!buckets[i].ptr || (norms && !norms[i].ptr)) return fail(SLICQ_E_INVALID, "null bucket pointer");
     cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
@@ -741,6 +742,7 @@ int inverse_impl(const slicq_plan* p, const slicq_bucket_view* buckets, const sl
     if (n_rows * n_slices > 0x7fffffffLL) return fail(SLICQ_E_INVALID, "too many (row,slice) units");
     if (scratch_bytes < slicq_scratch_bytes(p, n_rows, n_slices, 1) || !scratch)
         return fail(SLICQ_E_SCRATCH, "scratch buffer too small (see slicq_scratch_bytes)");
+    if (reinterpret_cast<uintptr_t>(scratch) & 15) return fail(SLICQ_E_SCRATCH, "scratch buffer must be 16-byte aligned");
     for (size_t i = 0; i < p->buckets.size(); ++i)
         if (!buckets[i].ptr) return fail(SLICQ_E_INVALID, "null bucket pointer");
     cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
