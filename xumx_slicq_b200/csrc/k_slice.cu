@@ -33,6 +33,15 @@
 #endif
 // tuning experiments only (results invalid): bit 0 skips the load phases of the synthesis slice kernel, bit 1 pass A,
 // bit 2 pass B, bit 3 the output stores
+// CTAs ahead whose input a CTA asks L2 to fetch while it transforms its own (0 = off).  Swept on the synthesis kernel:
+// 32 / 64 / 96 / 128 / 148 / 208 / 296 / 592 CTAs ahead = 0.520 / 0.505 / 0.506 / 0.511 / 0.512 / 0.521 / 0.545 / 0.620 ms (off: 0.545;
+// 296 CTAs are resident: further ahead the lines are evicted again before they are used)
+#ifndef SLICQ_PF_AHEAD
+#define SLICQ_PF_AHEAD 80
+#endif
+#ifndef SLICQ_PF_FWD
+#define SLICQ_PF_FWD 80
+#endif
 #ifndef SLICQ_DBG_SKIP
 #define SLICQ_DBG_SKIP 0
 #endif
@@ -135,6 +144,17 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_fwd_kernel(c
     const int e_lo = p.t.tw_lo >> 1, e_hi = (p.t.tw_hi + 1) >> 1;       // sample pairs with a non-zero window
     const long long sa = s0 + 2 * e_lo, sb = s0 + 2 * e_hi;             // x range touched by the window support
     const bool fast = sa >= 0 && sb <= p.T && ((reinterpret_cast<uintptr_t>(xr + s0) & 7) == 0);
+#if SLICQ_PF_FWD > 0
+    if (blockIdx.x + SLICQ_PF_FWD < gridDim.x) {
+        // the second half of the slice SLICQ_PF_FWD units ahead (its first half is the second half of its left neighbour)
+        const int rs2 = rs + SLICQ_PF_FWD;
+        const int row2 = rs2 / p.S, k2 = rs2 - row2 * p.S;
+        const long long a = (p.k0 + k2) * (long long)p.t.hop - p.t0;          // x index of the middle of that slice
+        const float* __restrict__ x2r = p.x + row2 * p.x_row_stride;
+        for (long long i = a + 32LL * threadIdx.x; i < a + p.t.hop; i += 32LL * NT)
+            if (i >= 0 && i < p.T) prefetch_l2(x2r + i);
+    }
+#endif
     // ---- windowed slice -> Z in natural order (coalesced loads; the zero part of the window is not read)
     if (fast) {
         const float2* __restrict__ x2 = reinterpret_cast<const float2*>(xr + s0);
@@ -289,6 +309,16 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
         if (tid < p.t.n_ex) xe = __ldg(p.t.ex + tid);
         float2 x2 = make_float2(0.f, 0.f), x3 = make_float2(0.f, 0.f);
         if (xe.x >= 0) { x2 = __ldg(Trow + xe.y); if (xe.z >= 0) x3 = __ldg(Trow + xe.z); }
+#if SLICQ_PF_AHEAD > 0
+        {   // while this CTA transforms, L2 fetches the row of the CTA that will run in this slot next (blockIdx + resident CTAs)
+            const int pj = pi + SLICQ_PF_AHEAD;
+            if (blockIdx.x + SLICQ_PF_AHEAD < gridDim.x) {
+                const int row2 = pj / p.par_cs, k2 = 2 * (pj - row2 * p.par_cs) + p.parity;
+                const float2* __restrict__ T2 = p.spec + (long long)(row2 * p.S + k2 - p.rs0) * p.spec_stride;
+                for (int i = tid; 16 * i < p.t.t_stride; i += NT) prefetch_l2(T2 + 16 * i);
+            }
+        }
+#endif
         mbar_wait(bar_, 0);
         // overflow entries: position f also receives T[off0] (+ T[off1]); entries have distinct f
         if (xe.x >= 0) { Z[xe.x].x += x2.x + x3.x; Z[xe.x].y += x2.y + x3.y; }

@@ -172,6 +172,13 @@ SLICQ_DEVFN void bulk_wait_read() {
 }
 #endif
 
+// software prefetch of a 128-byte line into L2 (a hint: no register, no scoreboard)
+#ifdef SLICQ_EMU
+static inline void prefetch_l2(const void*) {}
+#else
+SLICQ_DEVFN void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 #define SLICQ_MAX_BUCKETS 96
 #define SLICQ_MAX_M 292
 
