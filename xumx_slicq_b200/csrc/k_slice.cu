@@ -39,6 +39,9 @@
 #ifndef SLICQ_PF_AHEAD
 #define SLICQ_PF_AHEAD 80
 #endif
+#ifndef SLICQ_PF_BULK
+#define SLICQ_PF_BULK 1
+#endif
 #ifndef SLICQ_PF_FWD
 #define SLICQ_PF_FWD 80
 #endif
@@ -315,7 +318,11 @@ __global__ void __launch_bounds__(SLICQ_SLICE_THREADS, 2) slice_fft_inv_kernel(c
             if (blockIdx.x + SLICQ_PF_AHEAD < gridDim.x) {
                 const int row2 = pj / p.par_cs, k2 = 2 * (pj - row2 * p.par_cs) + p.parity;
                 const float2* __restrict__ T2 = p.spec + (long long)(row2 * p.S + k2 - p.rs0) * p.spec_stride;
+#if SLICQ_PF_BULK
+                if (tid == 32) bulk_prefetch_l2(T2, (unsigned)p.t.t_stride * 8u);      // rows are 16-byte aligned, t_stride is even
+#else
                 for (int i = tid; 16 * i < p.t.t_stride; i += NT) prefetch_l2(T2 + 16 * i);
+#endif
             }
         }
 #endif

@@ -178,6 +178,14 @@ static inline void prefetch_l2(const void*) {}
 #else
 SLICQ_DEVFN void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
+// the same for a whole 16-byte aligned range with ONE instruction (TMA engine; bytes a multiple of 16)
+#ifdef SLICQ_EMU
+static inline void bulk_prefetch_l2(const void*, unsigned) {}
+#else
+SLICQ_DEVFN void bulk_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#endif
 
 #define SLICQ_MAX_BUCKETS 96
 #define SLICQ_MAX_M 292
